@@ -1,0 +1,477 @@
+// Row-segmented CSR SpMM for sm_100a:  Y[i,:] = reduce_e val[e] * X[col[e],:]
+//
+// Replaces torch_sparse spmm_sum/spmm_mean as reached from the reference's
+// GCNConv / SAGEConv / SparseTensor.matmul call sites (arxiv_pyg/gnn.py:47,52,
+// 79,84; mag_pyg/gnn.py:162) and their backward (same kernel on the CSC view).
+//
+// Design (HBM/L2-bound gather, no tensor cores):
+//   * one warp per destination row; 32 (col,val) pairs are fetched with one
+//     coalesced load and broadcast by warp shuffle; each neighbour's feature
+//     row is gathered with 128-bit read-only loads, U*CH of them in flight per
+//     lane (8 x 16 B) so a warp keeps 4 KB of gather traffic outstanding;
+//   * narrow rows (K/4 < 32 vectors) fold several neighbours across the warp
+//     ("groups") and combine with shuffles, so K=40 keeps 30/32 lanes busy;
+//   * hub rows (degree > hub_threshold) are skipped here and split into
+//     fixed-length segments, one CTA each, reduced in a fixed order by a
+//     finalize kernel: no atomics anywhere, run-to-run deterministic;
+//   * epilogue fuses mean division, bias, and per-CTA partial column
+//     sum / sum-of-squares for the BatchNorm that follows the conv.
+#include "common.cuh"
+
+namespace b200gnn {
+
+constexpr int SPMM_THREADS = 256;
+constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+constexpr int SPMM_ROWS_PER_WARP = 8;
+constexpr int SPMM_ROWS_PER_CTA = SPMM_WARPS * SPMM_ROWS_PER_WARP;
+constexpr int SPMM_MAX_SLAB_FLOATS = 512;  // 32 lanes * CH(<=4) * W(<=4)
+
+struct SpmmParams {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  const float* X;
+  float* Y;
+  const float* bias;
+  float* stat_partial;
+  const int32_t* hub_rows;
+  const int32_t* hub_segptr;
+  float* hub_ws;
+  int64_t ldx, ldy;  // in floats
+  int32_t n_rows, K, nvec;
+  int32_t hub_threshold, seg_len, n_hub;
+  int32_t mean, stream_store, main_grid;
+};
+
+struct LaneMap {
+  int lpr, groups, g, l;
+  bool active;
+};
+
+__device__ __forceinline__ LaneMap make_lane_map(int nvec, int lane) {
+  LaneMap m;
+  if (nvec >= 32) {
+    m.lpr = 32; m.groups = 1; m.g = 0; m.l = lane; m.active = true;
+  } else {
+    m.lpr = nvec; m.groups = 32 / nvec; m.g = lane / nvec; m.l = lane - m.g * nvec;
+    m.active = m.g < m.groups;
+  }
+  return m;
+}
+
+// Accumulate edges [beg,end) of one row into per-lane partials for one column slab.
+template <typename V, int CH, bool HAS_VAL>
+__device__ __forceinline__ void walk_edges(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                           const V* __restrict__ Xv, size_t ldxv, int beg, int end,
+                                           int lane, const LaneMap& m, int slab_voff, int nvec, V (&acc)[CH]) {
+  constexpr int U = 8 / CH;
+  bool cvalid[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) cvalid[j] = m.active && (slab_voff + m.l + 32 * j < nvec);
+
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    int c = 0;
+    float v = HAS_VAL ? 0.f : 1.f;
+    if (e < end) {
+      c = __ldg(col + e);
+      if (HAS_VAL) v = __ldg(val + e);
+    }
+    const int cnt = min(32, end - base);
+    for (int t = 0; t < cnt; t += m.groups * U) {
+      V xv[U][CH];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = t + u * m.groups + m.g;
+        const int cc = __shfl_sync(FULL_MASK, c, idx & 31);
+        const float w = __shfl_sync(FULL_MASK, v, idx & 31);
+        const bool ok = idx < cnt;
+        vv[u] = ok ? w : 0.f;
+        const V* p = Xv + (size_t)cc * ldxv + slab_voff + m.l;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (ok && cvalid[j]) xv[u][j] = vldg(p + 32 * j);
+          else vzero(xv[u][j]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < CH; ++j) vfma(acc[j], vv[u], xv[u][j]);
+    }
+  }
+}
+
+template <typename V>
+__device__ __forceinline__ void group_reduce(V& a, const LaneMap& m) {
+  for (int gg = 1; gg < m.groups; ++gg) {
+    V o = vshfl_down(a, gg * m.lpr);
+    if (m.g == 0) vadd(a, o);
+  }
+}
+
+template <typename V>
+__device__ __forceinline__ V load_bias(const float* bias, int voff);
+template <> __device__ __forceinline__ float load_bias<float>(const float* b, int voff) { return __ldg(b + voff); }
+template <> __device__ __forceinline__ float2 load_bias<float2>(const float* b, int voff) {
+  return make_float2(__ldg(b + 2 * voff), __ldg(b + 2 * voff + 1));
+}
+template <> __device__ __forceinline__ float4 load_bias<float4>(const float* b, int voff) {
+  return make_float4(__ldg(b + 4 * voff), __ldg(b + 4 * voff + 1), __ldg(b + 4 * voff + 2), __ldg(b + 4 * voff + 3));
+}
+
+__device__ __forceinline__ void smem_accum(float* s, float* q, int voff, const float& a, const float& b) {
+  s[voff] += a; q[voff] += b;
+}
+__device__ __forceinline__ void smem_accum(float* s, float* q, int voff, const float2& a, const float2& b) {
+  s[2 * voff] += a.x; s[2 * voff + 1] += a.y; q[2 * voff] += b.x; q[2 * voff + 1] += b.y;
+}
+__device__ __forceinline__ void smem_accum(float* s, float* q, int voff, const float4& a, const float4& b) {
+  s[4 * voff] += a.x; s[4 * voff + 1] += a.y; s[4 * voff + 2] += a.z; s[4 * voff + 3] += a.w;
+  q[4 * voff] += b.x; q[4 * voff + 1] += b.y; q[4 * voff + 2] += b.z; q[4 * voff + 3] += b.w;
+}
+__device__ __forceinline__ void smem_add1(float* s, int voff, const float& a) { s[voff] += a; }
+__device__ __forceinline__ void smem_add1(float* s, int voff, const float2& a) { s[2 * voff] += a.x; s[2 * voff + 1] += a.y; }
+__device__ __forceinline__ void smem_add1(float* s, int voff, const float4& a) {
+  s[4 * voff] += a.x; s[4 * voff + 1] += a.y; s[4 * voff + 2] += a.z; s[4 * voff + 3] += a.w;
+}
+
+// ---------------------------------------------------------------- main kernel
+template <typename V, int CH, bool HAS_VAL, bool STATS>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmParams p) {
+  constexpr int W = VecTraits<V>::W;
+  __shared__ float s_stat[2 * SPMM_MAX_SLAB_FLOATS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LaneMap m = make_lane_map(p.nvec, lane);
+  const int slab_vecs = 32 * CH;
+  const int nslab = (p.nvec <= 32) ? 1 : (p.nvec + slab_vecs - 1) / slab_vecs;
+  const V* Xv = reinterpret_cast<const V*>(p.X);
+  V* Yv = reinterpret_cast<V*>(p.Y);
+  const size_t ldxv = (size_t)(p.ldx / W), ldyv = (size_t)(p.ldy / W);
+  constexpr bool do_stats = STATS;  // host guarantees nslab == 1 when set
+
+  V ssum[CH], ssq[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) { vzero(ssum[j]); vzero(ssq[j]); }
+
+  for (int rr = 0; rr < SPMM_ROWS_PER_WARP; ++rr) {
+    const int64_t row64 = (int64_t)blockIdx.x * SPMM_ROWS_PER_CTA + rr * SPMM_WARPS + warp;
+    if (row64 >= p.n_rows) break;
+    const int row = (int)row64;
+    const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+    const int deg = end - beg;
+    if (deg > p.hub_threshold) continue;  // split path owns this row (incl. its statistics)
+    for (int slab = 0; slab < nslab; ++slab) {
+      const int slab_voff = slab * slab_vecs;
+      V acc[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) vzero(acc[j]);
+      walk_edges<V, CH, HAS_VAL>(p.col, p.val, Xv, ldxv, beg, end, lane, m, slab_voff, p.nvec, acc);
+      if (m.groups > 1) group_reduce(acc[0], m);
+      if (m.g == 0 && m.active) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int voff = slab_voff + m.l + 32 * j;
+          if (voff < p.nvec) {
+            V y = acc[j];
+            if (p.mean) vdiv(y, (float)max(deg, 1));
+            if (p.bias) vadd(y, load_bias<V>(p.bias, voff));
+            V* dst = Yv + (size_t)row * ldyv + voff;
+            if (p.stream_store) vstcs(dst, y); else *dst = y;
+            if (do_stats) vstat(ssum[j], ssq[j], y);
+          }
+        }
+      }
+    }
+  }
+
+  if (do_stats) {
+    float* ss = s_stat;
+    float* sq = s_stat + p.K;
+    for (int i = threadIdx.x; i < 2 * p.K; i += SPMM_THREADS) s_stat[i] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < SPMM_WARPS; ++w) {  // fixed order => deterministic
+      if (warp == w && m.g == 0 && m.active) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int voff = m.l + 32 * j;
+          if (voff < p.nvec) smem_accum(ss, sq, voff, ssum[j], ssq[j]);
+        }
+      }
+      __syncthreads();
+    }
+    float* out = p.stat_partial + (size_t)blockIdx.x * 2 * p.K;
+    for (int i = threadIdx.x; i < 2 * p.K; i += SPMM_THREADS) out[i] = s_stat[i];
+  }
+}
+
+// ------------------------------------------------------- hub segment kernel
+// One CTA per segment of a hub row: 8 warps take contiguous sub-ranges, then
+// combine in warp order through shared memory; raw (un-normalised) partials go
+// to the workspace.
+template <typename V, int CH, bool HAS_VAL>
+__global__ void __launch_bounds__(SPMM_THREADS) spmm_hub_seg_kernel(const SpmmParams p) {
+  constexpr int W = VecTraits<V>::W;
+  __shared__ float s_buf[SPMM_MAX_SLAB_FLOATS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LaneMap m = make_lane_map(p.nvec, lane);
+  const int slab_vecs = 32 * CH;
+  const int nslab = (p.nvec <= 32) ? 1 : (p.nvec + slab_vecs - 1) / slab_vecs;
+  const V* Xv = reinterpret_cast<const V*>(p.X);
+  const size_t ldxv = (size_t)(p.ldx / W);
+
+  const int seg = blockIdx.x;
+  int lo = 0, hi = p.n_hub;  // largest h with hub_segptr[h] <= seg
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(p.hub_segptr + mid) <= seg) lo = mid; else hi = mid;
+  }
+  const int h = lo;
+  const int row = __ldg(p.hub_rows + h);
+  const int s = seg - __ldg(p.hub_segptr + h);
+  const int rbeg = __ldg(p.rowptr + row), rend = __ldg(p.rowptr + row + 1);
+  const int sbeg = rbeg + s * p.seg_len;
+  const int send = min(rend, sbeg + p.seg_len);
+  int per = (send - sbeg + SPMM_WARPS - 1) / SPMM_WARPS;
+  per = (per + 31) / 32 * 32;
+  const int wbeg = min(send, sbeg + warp * per);
+  const int wend = min(send, wbeg + per);
+
+  float* ws = p.hub_ws + (size_t)seg * p.K;
+  for (int slab = 0; slab < nslab; ++slab) {
+    const int slab_voff = slab * slab_vecs;
+    V acc[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) vzero(acc[j]);
+    walk_edges<V, CH, HAS_VAL>(p.col, p.val, Xv, ldxv, wbeg, wend, lane, m, slab_voff, p.nvec, acc);
+    if (m.groups > 1) group_reduce(acc[0], m);
+
+    for (int i = threadIdx.x; i < SPMM_MAX_SLAB_FLOATS; i += SPMM_THREADS) s_buf[i] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < SPMM_WARPS; ++w) {
+      if (warp == w && m.g == 0 && m.active) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int voff = slab_voff + m.l + 32 * j;
+          if (voff < p.nvec) smem_add1(s_buf, m.l + 32 * j, acc[j]);
+        }
+      }
+      __syncthreads();
+    }
+    const int slab_f0 = slab_voff * W;
+    const int slab_fn = min(slab_vecs * W, p.K - slab_f0);
+    for (int i = threadIdx.x; i < slab_fn; i += SPMM_THREADS) ws[slab_f0 + i] = s_buf[i];
+    __syncthreads();
+  }
+}
+
+// Sum a hub row's segment partials in segment order, apply the epilogue.
+__global__ void __launch_bounds__(256) spmm_hub_finalize_kernel(const SpmmParams p) {
+  const int h = blockIdx.x;
+  const int row = __ldg(p.hub_rows + h);
+  const int s0 = __ldg(p.hub_segptr + h), s1 = __ldg(p.hub_segptr + h + 1);
+  const int deg = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
+  float* stat = p.stat_partial ? p.stat_partial + (size_t)(p.main_grid + h) * 2 * p.K : nullptr;
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+    float acc = 0.f;
+    for (int s = s0; s < s1; ++s) acc += p.hub_ws[(size_t)s * p.K + k];
+    if (p.mean) acc /= (float)max(deg, 1);
+    if (p.bias) acc += __ldg(p.bias + k);
+    p.Y[(size_t)row * p.ldy + k] = acc;
+    if (stat) { stat[k] = acc; stat[p.K + k] = acc * acc; }
+  }
+}
+
+// Column sum / sum-of-squares of a dense [n_rows,K] matrix into `slots`
+// deterministic partials (used when the producer could not fuse them).
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ Y, int64_t ldy, int64_t n_rows,
+                                                        int K, float* __restrict__ partial, int slots) {
+  const int slot = blockIdx.x;
+  const int64_t per = (n_rows + slots - 1) / slots;
+  const int64_t r0 = (int64_t)slot * per, r1 = min(n_rows, r0 + per);
+  float* out = partial + (size_t)slot * 2 * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float y = Y[(size_t)r * ldy + k];
+      s += y; q = fmaf(y, y, q);
+    }
+    out[k] = s; out[K + k] = q;
+  }
+}
+
+template <typename V, int CH>
+static int launch_spmm(const SpmmParams& p, int n_seg, cudaStream_t st) {
+  int rc;
+  const bool stats = p.stat_partial != nullptr;
+  if (p.val) {
+    if (stats) spmm_rows_kernel<V, CH, true, true><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
+    else spmm_rows_kernel<V, CH, true, false><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+    if (n_seg > 0) {
+      spmm_hub_seg_kernel<V, CH, true><<<n_seg, SPMM_THREADS, 0, st>>>(p);
+      if ((rc = check_launch())) return rc;
+    }
+  } else {
+    if (stats) spmm_rows_kernel<V, CH, false, true><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
+    else spmm_rows_kernel<V, CH, false, false><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+    if (n_seg > 0) {
+      spmm_hub_seg_kernel<V, CH, false><<<n_seg, SPMM_THREADS, 0, st>>>(p);
+      if ((rc = check_launch())) return rc;
+    }
+  }
+  if (p.n_hub > 0) {
+    spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}
+
+template <typename V>
+static int dispatch_ch(const SpmmParams& p, int n_seg, cudaStream_t st) {
+  if (p.nvec <= 32) return launch_spmm<V, 1>(p, n_seg, st);
+  if (p.nvec <= 64) return launch_spmm<V, 2>(p, n_seg, st);
+  return launch_spmm<V, 4>(p, n_seg, st);
+}
+
+// ------------------------------------------------------------ hub plan kernels
+__global__ void __launch_bounds__(1024) hub_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
+                                                         int32_t thr, int32_t seg_len, int32_t* __restrict__ out) {
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int nh = 0, ns = 0;
+  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const int deg = rowptr[r + 1] - rowptr[r];
+    if (deg > thr) { nh += 1; ns += (deg + seg_len - 1) / seg_len; }
+  }
+  atomicAdd(&s_cnt[0], nh);
+  atomicAdd(&s_cnt[1], ns);
+  __syncthreads();
+  if (threadIdx.x < 2) out[threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// Ordered compaction of hub rows (ascending row id) with their segment offsets.
+__global__ void __launch_bounds__(1024) hub_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
+                                                        int32_t thr, int32_t seg_len, int32_t* __restrict__ hub_rows,
+                                                        int32_t* __restrict__ hub_segptr, int64_t n_hub) {
+  __shared__ int s_wflag[32], s_wseg[32];
+  __shared__ int s_base[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = 0; }
+  __syncthreads();
+  for (int64_t r0 = 0; r0 < n_rows; r0 += blockDim.x) {
+    const int64_t r = r0 + threadIdx.x;
+    int flag = 0, segs = 0;
+    if (r < n_rows) {
+      const int deg = rowptr[r + 1] - rowptr[r];
+      if (deg > thr) { flag = 1; segs = (deg + seg_len - 1) / seg_len; }
+    }
+    int f = flag, s = segs;  // inclusive warp scans
+    for (int d = 1; d < 32; d <<= 1) {
+      const int of = __shfl_up_sync(FULL_MASK, f, d), os = __shfl_up_sync(FULL_MASK, s, d);
+      if (lane >= d) { f += of; s += os; }
+    }
+    if (lane == 31) { s_wflag[warp] = f; s_wseg[warp] = s; }
+    __syncthreads();
+    if (warp == 0) {
+      int wf = s_wflag[lane], wsg = s_wseg[lane];
+      int xf = wf, xs = wsg;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int of = __shfl_up_sync(FULL_MASK, xf, d), os = __shfl_up_sync(FULL_MASK, xs, d);
+        if (lane >= d) { xf += of; xs += os; }
+      }
+      s_wflag[lane] = xf - wf;  // exclusive warp offsets
+      s_wseg[lane] = xs - wsg;
+    }
+    __syncthreads();
+    const int pos = s_base[0] + s_wflag[warp] + f - flag;
+    const int soff = s_base[1] + s_wseg[warp] + s - segs;
+    if (flag && pos < n_hub) { hub_rows[pos] = (int32_t)r; hub_segptr[pos] = soff; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+      s_base[0] = pos + flag;
+      s_base[1] = soff + segs;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) hub_segptr[n_hub] = s_base[1];
+}
+
+}  // namespace b200gnn
+
+using namespace b200gnn;
+
+extern "C" int b200gnn_csr_hub_count(const int32_t* rowptr, int64_t n_rows, int32_t hub_threshold, int32_t seg_len,
+                                     int32_t* counts_out, void* stream) {
+  if (!rowptr || !counts_out || n_rows < 0 || hub_threshold < 0 || seg_len <= 0) return B200GNN_ERR_BAD_ARG;
+  hub_count_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowptr, n_rows, hub_threshold, seg_len, counts_out);
+  return check_launch();
+}
+
+extern "C" int b200gnn_csr_hub_fill(const int32_t* rowptr, int64_t n_rows, int32_t hub_threshold, int32_t seg_len,
+                                    int32_t* hub_rows, int32_t* hub_segptr, int64_t n_hub, void* stream) {
+  if (!rowptr || !hub_segptr || n_rows < 0 || n_hub < 0 || hub_threshold < 0 || seg_len <= 0) return B200GNN_ERR_BAD_ARG;
+  if (n_hub > 0 && !hub_rows) return B200GNN_ERR_BAD_ARG;
+  hub_fill_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowptr, n_rows, hub_threshold, seg_len, hub_rows, hub_segptr, n_hub);
+  return check_launch();
+}
+
+extern "C" int64_t b200gnn_spmm_stat_slots(int64_t n_rows, int64_t n_hub) {
+  return (n_rows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA + n_hub;
+}
+
+extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                                    int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t n_src, int64_t K,
+                                    int reduce, const float* bias, float* stat_partial, int32_t hub_threshold,
+                                    int32_t seg_len, const int32_t* hub_rows, const int32_t* hub_segptr,
+                                    int64_t n_hub, int64_t n_seg, float* hub_workspace, void* stream) {
+  if (n_rows < 0 || n_src < 0 || K <= 0 || n_rows >= INT32_MAX || n_src >= INT32_MAX || K > (1 << 20))
+    return B200GNN_ERR_BAD_ARG;
+  if (reduce != B200GNN_REDUCE_SUM && reduce != B200GNN_REDUCE_MEAN) return B200GNN_ERR_BAD_ARG;
+  if (n_rows == 0) return B200GNN_OK;
+  if (!rowptr || !Y || ldy < K) return B200GNN_ERR_BAD_ARG;
+  if (n_src > 0 && (!X || !col || ldx < K)) return B200GNN_ERR_BAD_ARG;
+  if (n_hub < 0 || n_seg < 0 || hub_threshold < 0) return B200GNN_ERR_BAD_ARG;
+  if (n_hub > 0 && (!hub_rows || !hub_segptr || !hub_workspace || seg_len <= 0 || n_seg < n_hub))
+    return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  SpmmParams p;
+  p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.Y = Y; p.bias = bias;
+  p.stat_partial = stat_partial;
+  p.hub_rows = hub_rows; p.hub_segptr = hub_segptr; p.hub_ws = hub_workspace;
+  p.ldx = ldx; p.ldy = ldy;
+  p.n_rows = (int32_t)n_rows; p.K = (int32_t)K;
+  p.hub_threshold = hub_threshold; p.seg_len = seg_len; p.n_hub = (int32_t)n_hub;
+  p.mean = reduce == B200GNN_REDUCE_MEAN;
+  p.stream_store = (n_rows * K * 4 > (int64_t)64 << 20) ? 1 : 0;
+  p.main_grid = (int32_t)((n_rows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA);
+
+  // widest vector type the layout allows
+  int W = 1;
+  if (K % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned_to(X, 16) && aligned_to(Y, 16)) W = 4;
+  else if (K % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && aligned_to(X, 8) && aligned_to(Y, 8)) W = 2;
+  p.nvec = (int32_t)(K / W);
+  const int ch = p.nvec <= 32 ? 1 : (p.nvec <= 64 ? 2 : 4);
+  const bool single_slab = p.nvec <= 32 * ch;
+  float* fused_stats = stat_partial;
+  if (!single_slab) p.stat_partial = nullptr;  // stats by a separate pass below
+
+  int rc;
+  if (W == 4) rc = dispatch_ch<float4>(p, (int)n_seg, st);
+  else if (W == 2) rc = dispatch_ch<float2>(p, (int)n_seg, st);
+  else rc = dispatch_ch<float>(p, (int)n_seg, st);
+  if (rc) return rc;
+
+  if (fused_stats && !single_slab) {
+    const int slots = (int)b200gnn_spmm_stat_slots(n_rows, n_hub);
+    col_stats_kernel<<<slots, 256, 0, st>>>(Y, ldy, n_rows, (int)K, fused_stats, slots);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}

@@ -1,0 +1,103 @@
+"""ctypes binding of ``libb200gnn.so`` — the C ABI declared in ``include/b200gnn.h``.
+
+The library is the product: if it is missing or a symbol is absent this module
+raises; nothing in this package falls back to PyTorch or CPU arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libb200gnn.so"
+
+OK = 0
+REDUCE_SUM = 0
+REDUCE_MEAN = 1
+
+_i32p = C.c_void_p
+_f32p = C.c_void_p
+_ptr = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_int = C.c_int
+_f32 = C.c_float
+_u64 = C.c_uint64
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against the header.
+SIGNATURES = {
+    "b200gnn_abi_version": (_int, []),
+    "b200gnn_error_string": (C.c_char_p, [_int]),
+    "b200gnn_last_cuda_error": (C.c_char_p, []),
+    "b200gnn_launch_count": (_i64, []),
+    "b200gnn_reset_launch_count": (None, []),
+    "b200gnn_csr_hub_count": (_int, [_i32p, _i64, _i32, _i32, _i32p, _ptr]),
+    "b200gnn_csr_hub_fill": (_int, [_i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _ptr]),
+    "b200gnn_spmm_stat_slots": (_i64, [_i64, _i64]),
+    "b200gnn_spmm_csr_f32": (_int, [_i32p, _i32p, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _int,
+                                    _f32p, _f32p, _i32, _i32, _i32p, _i32p, _i64, _i64, _f32p, _ptr]),
+}
+
+_lib = None
+
+
+class B200GnnError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200GnnError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the b200gnn operators.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200gnn_abi_version() != 1:
+        raise B200GnnError("libb200gnn.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        lib = load()
+        msg = lib.b200gnn_error_string(rc).decode()
+        if rc == -3:
+            msg += ": " + lib.b200gnn_last_cuda_error().decode()
+        raise B200GnnError(f"{what} failed: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dptr(t: torch.Tensor | None, dtype: torch.dtype, name: str) -> int | None:
+    """Device pointer of a contiguous CUDA tensor of the given dtype (None passes through)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise B200GnnError(f"{name}: b200gnn operators need CUDA tensors (got {t.device}); there is no CPU fallback")
+    if t.dtype != dtype:
+        raise B200GnnError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B200GnnError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().b200gnn_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().b200gnn_reset_launch_count()

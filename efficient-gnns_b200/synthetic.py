@@ -1,0 +1,79 @@
+"""Seeded synthetic datasets of the shapes the reference trains on.
+
+There is no network for ogbn-arxiv / ogbn-mag, so the benchmark and the tests use
+graphs with the same node/edge counts, feature widths and a citation-like heavy
+in-degree tail.  Everything is generated on the CPU with an explicit
+``torch.Generator`` so the GPU box and this container produce identical inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict
+
+import torch
+
+ARXIV = dict(num_nodes=169_343, num_edges=1_166_243, num_features=128, num_classes=40,
+             n_train=90_941, n_valid=29_799, n_test=48_603, teacher_dim=750)
+PLUMBING = dict(num_nodes=10_000, num_edges=50_000, num_features=64, num_classes=40,
+                n_train=5_000, n_valid=2_000, n_test=3_000, teacher_dim=96)
+
+
+def skewed_edges(num_nodes: int, num_edges: int, seed: int = 0, p_local: float = 0.0,
+                 num_blocks: int = 8) -> torch.Tensor:
+    """Directed edge_index [2,E]: src ~ U[0,N), dst = floor(N*u^3); unique, no self-loops, exactly E edges.
+
+    ``p_local``: probability of redrawing dst inside src's block of ceil(N/num_blocks) contiguous ids
+    (locality knob for halo experiments; 0 = none)."""
+    g = torch.Generator().manual_seed(seed)
+    N = num_nodes
+    keys = torch.empty(0, dtype=torch.long)
+    while keys.numel() < num_edges:
+        need = num_edges - keys.numel()
+        m = int(need * 1.3) + 1024
+        src = torch.randint(0, N, (m,), generator=g)
+        u = torch.rand(m, generator=g, dtype=torch.float64)
+        dst = (u.pow(3) * N).long().clamp_(max=N - 1)
+        if p_local > 0:
+            blk = -(-N // num_blocks)
+            loc = torch.rand(m, generator=g) < p_local
+            lo = (src // blk) * blk
+            span = torch.minimum(torch.full_like(lo, blk), N - lo)
+            dloc = lo + (torch.rand(m, generator=g, dtype=torch.float64) * span).long()
+            dst = torch.where(loc, dloc, dst)
+        ok = src != dst
+        new = (src[ok] * N + dst[ok])
+        # keep first occurrences, preserving draw order
+        allk = torch.cat([keys, new])
+        uniq, inv = torch.unique(allk, return_inverse=True)
+        first = torch.full((uniq.numel(),), allk.numel(), dtype=torch.long)
+        first.scatter_reduce_(0, inv, torch.arange(allk.numel()), reduce="amin")
+        keys = allk[torch.sort(first).values][:num_edges]
+    return torch.stack([keys // N, keys % N])
+
+
+@dataclass
+class NodeDataset:
+    """What ``PygNodePropPredDataset('ogbn-arxiv')[0]`` + ``get_idx_split()`` carry (arxiv_pyg/gnn.py:236-244)."""
+    num_nodes: int
+    x: torch.Tensor            # [N,F] fp32
+    y: torch.Tensor            # [N,1] int64
+    edge_index: torch.Tensor   # [2,E] int64, directed, unique
+    split_idx: Dict[str, torch.Tensor]
+    num_classes: int
+    teacher_logits: torch.Tensor   # [N,C]   stands in for arxiv_dgl/logits/<expt>/<seed>.pt
+    teacher_feat: torch.Tensor     # [N,750] stands in for arxiv_dgl/features/<expt>/<seed>.pt
+
+
+def make_node_dataset(shape: dict = ARXIV, seed: int = 0, p_local: float = 0.0) -> NodeDataset:
+    g = torch.Generator().manual_seed(seed + 1)
+    N, F, Cn = shape["num_nodes"], shape["num_features"], shape["num_classes"]
+    ei = skewed_edges(N, shape["num_edges"], seed, p_local)
+    x = torch.randn(N, F, generator=g)
+    y = torch.randint(0, Cn, (N, 1), generator=g)
+    perm = torch.randperm(N, generator=g)
+    a, b = shape["n_train"], shape["n_train"] + shape["n_valid"]
+    split = {"train": perm[:a].sort().values, "valid": perm[a:b].sort().values,
+             "test": perm[b:b + shape["n_test"]].sort().values}
+    t_logits = torch.randn(N, Cn, generator=g) * 2.0
+    t_feat = torch.relu(torch.randn(N, shape["teacher_dim"], generator=g))
+    return NodeDataset(N, x, y, ei, split, Cn, t_logits, t_feat)

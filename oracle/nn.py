@@ -1,0 +1,74 @@
+"""Layer / model forwards restated functionally (weights passed in), CPU PyTorch.
+
+GCNConv / SAGEConv semantics follow SURVEY.md Appendix A.2 / A.3 as used by the reference's
+``GCN`` / ``SAGE`` modules (arxiv_pyg/gnn.py:23-85); BatchNorm1d / dropout per A.8.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def gcn_conv(x, rowptr, col, val, weight, bias, form: str = "csr"):
+    """out = Â (x W) + b  — transform first, then aggregate (PyG GCNConv, SparseTensor path). weight: [in,out]."""
+    h = x @ weight
+    n = rowptr.numel() - 1
+    if form == "csr":
+        out = ops.spmm_csr(rowptr, col, val, h, n, "sum")
+    else:
+        row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+        out = ops.spmm_scatter(row, col, val, h, n, "sum")
+    return out if bias is None else out + bias
+
+
+def sage_conv(x, rowptr, col, w_l, b_l, w_r, form: str = "csr"):
+    """out = lin_l(mean_j x_j) + lin_r(x) (PyG SAGEConv; w_l/w_r are nn.Linear weights [out,in])."""
+    n = rowptr.numel() - 1
+    if form == "csr":
+        agg = ops.spmm_csr(rowptr, col, None, x, n, "mean")
+    else:
+        row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+        agg = ops.spmm_scatter(row, col, None, x, n, "mean")
+    return F.linear(agg, w_l, b_l) + F.linear(x, w_r)
+
+
+def batch_norm_train(x, gamma, beta, eps: float = 1e-5):
+    """BatchNorm1d in training mode: biased batch variance for the normalisation."""
+    mean = x.mean(0)
+    var = x.var(0, unbiased=False)
+    return (x - mean) / torch.sqrt(var + eps) * gamma + beta
+
+
+def gcn_forward(x, rowptr, col, val, weights: List[torch.Tensor], biases: List[torch.Tensor],
+                bn_gamma: List[torch.Tensor], bn_beta: List[torch.Tensor],
+                dropout_masks: Optional[List[torch.Tensor]] = None, p: float = 0.5, form: str = "csr"):
+    """GCN.forward (arxiv_pyg/gnn.py:45-53) in training mode. ``dropout_masks[i]`` (bool keep-mask) replaces the
+    RNG so CUDA and oracle share the mask; None => no dropout. Returns (logits, last hidden = model.out_feat)."""
+    hidden = None
+    for i in range(len(weights) - 1):
+        x = gcn_conv(x, rowptr, col, val, weights[i], biases[i], form)
+        x = batch_norm_train(x, bn_gamma[i], bn_beta[i])
+        x = torch.relu(x)
+        if dropout_masks is not None:
+            x = x * dropout_masks[i].to(x.dtype) / (1.0 - p)
+        hidden = x
+    return gcn_conv(x, rowptr, col, val, weights[-1], biases[-1], form), hidden
+
+
+def sage_forward(x, rowptr, col, params: List[dict], bn_gamma, bn_beta, dropout_masks=None, p: float = 0.5):
+    """SAGE.forward (arxiv_pyg/gnn.py:77-85); params[i] = dict(w_l, b_l, w_r)."""
+    hidden = None
+    for i in range(len(params) - 1):
+        q = params[i]
+        x = sage_conv(x, rowptr, col, q["w_l"], q["b_l"], q["w_r"])
+        x = batch_norm_train(x, bn_gamma[i], bn_beta[i])
+        x = torch.relu(x)
+        if dropout_masks is not None:
+            x = x * dropout_masks[i].to(x.dtype) / (1.0 - p)
+        hidden = x
+    q = params[-1]
+    return sage_conv(x, rowptr, col, q["w_l"], q["b_l"], q["w_r"]), hidden

@@ -1,0 +1,186 @@
+"""Generate golden fixtures by running the REFERENCE's own Python files, unmodified, in the build container.
+
+    python tests/golden/make_golden.py        (needs /root/reference; not run on the GPU box)
+
+/root/reference's hot-path arithmetic lives in torch_geometric / torch_sparse, which are not installed,
+so `arxiv_pyg/criterion.py` and `arxiv_pyg/gnn.py` are imported on top of minimal stand-in modules whose
+operators come from oracle/ (the CPU restatement).  What the fixtures therefore pin:
+  * criterion_*.pt  — outputs/gradients of the reference's six criteria (kd, fitnet, at, gpw, lpw, nce)
+    computed BY THE REFERENCE FILE; only `softmax` (lpw) is a restated dependency.
+  * model_*.pt      — logits / out_feat / parameter gradients of the reference's `GCN` and `SAGE` classes
+    computed BY THE REFERENCE FILE on restated GCNConv / SAGEConv operators.
+Both oracle/ (tests, -m "not gpu") and the CUDA path (tests, -m gpu) must reproduce them.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+from oracle import graph as og, ops as oo  # noqa: E402
+
+
+# ----------------------------------------------------------------------------- stand-in modules
+class _AdjT:
+    """What the restated convs need from a SparseTensor: CSR arrays (+ cached GCN normalisation)."""
+
+    def __init__(self, rowptr, col, n):
+        self.rowptr, self.col, self.n = rowptr, col, n
+        self._gcn = None
+
+    def gcn(self):
+        if self._gcn is None:
+            row = np.repeat(np.arange(self.n), np.diff(self.rowptr.numpy()))
+            r, c, v = og.gcn_norm(row, self.col.numpy(), self.n)
+            self._gcn = (torch.from_numpy(og.ind2ptr(r, self.n)), torch.from_numpy(c), torch.from_numpy(v))
+        return self._gcn
+
+
+class GCNConv(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, cached=False):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = (6.0 / (self.weight.size(0) + self.weight.size(1))) ** 0.5
+        torch.nn.init.uniform_(self.weight, -a, a)
+        torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x, adj_t):
+        rowptr, col, val = adj_t.gcn()
+        return oo.spmm_scatter(torch.repeat_interleave(torch.arange(adj_t.n), rowptr[1:] - rowptr[:-1]), col, val,
+                               x @ self.weight, adj_t.n, "sum") + self.bias
+
+
+class SAGEConv(torch.nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin_l = torch.nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = torch.nn.Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x, adj_t):
+        row = torch.repeat_interleave(torch.arange(adj_t.n), adj_t.rowptr[1:] - adj_t.rowptr[:-1])
+        agg = oo.spmm_scatter(row, adj_t.col, None, x, adj_t.n, "mean")
+        return self.lin_l(agg) + self.lin_r(x)
+
+
+def install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    na = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("stub"))  # noqa: E731
+    tg = mod("torch_geometric")
+    tg.utils = mod("torch_geometric.utils", softmax=oo.segment_softmax, to_dense_adj=na, negative_sampling=na,
+                   add_self_loops=na,
+                   subgraph=lambda s, ei, relabel_nodes=False: (torch.from_numpy(
+                       og.subgraph(s.numpy(), ei.numpy(), relabel_nodes)[0]), None))
+    tg.nn = mod("torch_geometric.nn", GCNConv=GCNConv, SAGEConv=SAGEConv)
+    tg.transforms = mod("torch_geometric.transforms", ToSparseTensor=na)
+    ogb = mod("ogb")
+    ogb.nodeproppred = mod("ogb.nodeproppred", PygNodePropPredDataset=na, Evaluator=na)
+
+
+def small_graph(n=240, e=1400, seed=3):
+    from efficient_gnns_b200.synthetic import skewed_edges
+    ei = skewed_edges(n, e, seed).numpy()
+    row, col, _ = og.to_sparse_adj_t(ei, n)
+    r, c = og.to_symmetric(row, col, n)
+    return ei, r, c, og.ind2ptr(r, n)
+
+
+def main():
+    assert REF.exists(), "/root/reference is needed to regenerate the fixtures"
+    install_stubs()
+    sys.path.insert(0, str(REF / "arxiv_pyg"))
+    crit = importlib.import_module("criterion")
+    gnn = importlib.import_module("gnn")
+
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(11)
+    n, C, Fs, Ft = 240, 8, 24, 40
+    ei, r, c, rowptr = small_graph(n)
+    edge_index = torch.from_numpy(np.stack([r, c]))          # = torch.stack(adj_t.coo()[:2]) of the symmetric adj
+    train_idx = torch.randperm(n, generator=g)[:150].sort().values
+    sub_ei = torch.from_numpy(og.subgraph(train_idx.numpy(), edge_index.numpy(), True)[0])
+    nt = train_idx.numel()
+
+    logits = torch.randn(nt, C, generator=g)
+    labels = torch.randint(0, C, (nt,), generator=g)
+    t_logits = torch.randn(nt, C, generator=g) * 2
+    feat = torch.randn(nt, Fs, generator=g).relu() + 0.01
+    t_feat = torch.randn(nt, Ft, generator=g).relu() + 0.01
+    same_t_feat = torch.randn(nt, Fs, generator=g)          # fitnet / nce / gpw need equal widths after projection
+    inds = torch.randperm(nt, generator=g)[:64]
+
+    cases = {}
+
+    def run(name, fn, feats_need_grad=True):
+        z = logits.clone().requires_grad_(True)
+        f = feat.clone().requires_grad_(feats_need_grad)
+        out = fn(z, f)
+        loss = out[0]
+        grads = torch.autograd.grad(loss, [z] + ([f] if feats_need_grad else []), allow_unused=True)
+        cases[name] = dict(loss=out[0].detach(), loss_cls=out[1].detach(), loss_aux=out[2].detach(),
+                           d_logits=grads[0], d_feat=grads[1] if feats_need_grad else None)
+
+    run("kd", lambda z, f: crit.kd_criterion(z, labels, t_logits, 0.9, 4.0), False)
+    run("fitnet", lambda z, f: crit.fitnet_criterion(z, labels, f, same_t_feat, 1000))
+    run("at", lambda z, f: crit.at_criterion(z, labels, f, t_feat, 1000))
+    for k in ("cosine", "poly", "l2", "rbf"):
+        run(f"gpw_{k}", lambda z, f, k=k: crit.gpw_criterion(z, labels, f, t_feat, k, 1.0, 10 ** 9))
+        run(f"lpw_{k}", lambda z, f, k=k: crit.lpw_criterion(z, labels, f, t_feat, sub_ei, k, 100))
+    # sampled variants: seed numpy exactly like the reference's seed() does, record the draw
+    np.random.seed(5)
+    draw = torch.from_numpy(np.random.choice(nt, 64, replace=False))
+    np.random.seed(5)
+    run("gpw_cosine_sampled", lambda z, f: crit.gpw_criterion(z, labels, f, t_feat, "cosine", 1.0, 64))
+    np.random.seed(5)
+    run("nce_sampled", lambda z, f: crit.nce_criterion(z, labels, f, same_t_feat, 0.5, 0.075, 64))
+    run("nce_full", lambda z, f: crit.nce_criterion(z, labels, f, same_t_feat, 0.5, 0.075, 10 ** 9))
+
+    torch.save(dict(inputs=dict(logits=logits, labels=labels, t_logits=t_logits, feat=feat, t_feat=t_feat,
+                                same_t_feat=same_t_feat, sub_edge_index=sub_ei, np_seed=5, np_draw=draw),
+                    cases=cases), OUT / "criterion_arxiv.pt")
+
+    # ---- models: the reference's GCN / SAGE classes
+    x = torch.randn(n, 16, generator=g)
+    adj = _AdjT(torch.from_numpy(rowptr), torch.from_numpy(c), n)
+    models = {}
+    for name, cls in (("gcn", gnn.GCN), ("sage", gnn.SAGE)):
+        torch.manual_seed(1)
+        m = cls(16, 32, C, 3, 0.0)  # dropout 0: the mask is the only thing that cannot be shared
+        m.train()
+        out = m(x, adj)
+        y = torch.randint(0, C, (n,), generator=g)
+        loss = torch.nn.functional.cross_entropy(out[train_idx], y[train_idx])
+        loss.backward()
+        models[name] = dict(state={k: v.detach().clone() for k, v in m.state_dict().items()},
+                            logits_train=out.detach(), out_feat=m.out_feat.detach(), y=y, loss=loss.detach(),
+                            grads={k: p.grad.detach().clone() for k, p in m.named_parameters()})
+        m.eval()
+        models[name]["logits_eval"] = m(x, adj).detach()
+    torch.save(dict(edge_index_directed=torch.from_numpy(ei), sym_row=torch.from_numpy(r), sym_col=torch.from_numpy(c),
+                    x=x, train_idx=train_idx, sub_edge_index=sub_ei, models=models), OUT / "model_arxiv.pt")
+    print("wrote", [p.name for p in OUT.glob("*.pt")])
+
+
+if __name__ == "__main__":
+    main()
