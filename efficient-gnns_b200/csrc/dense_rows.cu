@@ -1,0 +1,377 @@
+// Row-major [n_rows, K] fp32 passes that sit between the aggregations of a student GNN layer
+// (arxiv_pyg/gnn.py:46-50: conv -> BatchNorm1d -> ReLU -> dropout) and their backward.
+// All are HBM-bound streaming kernels: 128-bit accesses, per-CTA deterministic partial
+// reductions (no atomics), grid sized to a multiple of the 148 SMs.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace b200gnn {
+
+constexpr int ROWS_THREADS = 256;
+
+// thread -> (vector column cv, row group rg); rows_per_iter row groups cover 256 threads.
+struct RowMap {
+  int nvec, rows_per_iter, cv, rg;
+  bool active;
+};
+__device__ __forceinline__ RowMap make_row_map(int K) {
+  RowMap m;
+  m.nvec = K >> 2;
+  m.rows_per_iter = ROWS_THREADS / m.nvec;
+  m.rg = threadIdx.x / m.nvec;
+  m.cv = threadIdx.x - m.rg * m.nvec;
+  m.active = m.rg < m.rows_per_iter;
+  return m;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Deterministic cross-row-group reduction of two float4 accumulators into partial[slot][2][K].
+__device__ __forceinline__ void reduce_store_2xK(const RowMap& m, int K, float4 a, float4 b, float* smem /*2*K*/,
+                                                 float* out) {
+  for (int i = threadIdx.x; i < 2 * K; i += ROWS_THREADS) smem[i] = 0.f;
+  __syncthreads();
+  for (int g = 0; g < m.rows_per_iter; ++g) {
+    if (m.active && m.rg == g) {
+      float* s = smem + 4 * m.cv;
+      float* q = smem + K + 4 * m.cv;
+      s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+      q[0] += b.x; q[1] += b.y; q[2] += b.z; q[3] += b.w;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 2 * K; i += ROWS_THREADS) out[i] = smem[i];
+}
+
+// ---------------------------------------------------------------- column statistics
+__global__ void __launch_bounds__(ROWS_THREADS) col_stats4_kernel(const float* __restrict__ Y, int64_t n_rows, int K,
+                                                                  float* __restrict__ partial, int slots) {
+  extern __shared__ float smem[];
+  const RowMap m = make_row_map(K);
+  const int64_t per = (n_rows + slots - 1) / slots;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n_rows, r0 + per);
+  float4 s = make_float4(0, 0, 0, 0), q = s;
+  if (m.active)
+    for (int64_t r = r0 + m.rg; r < r1; r += m.rows_per_iter) {
+      const float4 y = ld4(Y + (size_t)r * K + 4 * m.cv);
+      vstat(s, q, y);
+    }
+  reduce_store_2xK(m, K, s, q, smem, partial + (size_t)blockIdx.x * 2 * K);
+}
+
+// ---------------------------------------------------------------- BatchNorm finalize (training mode)
+// partial[slots][2][K] -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale; running stats updated
+// like nn.BatchNorm1d (momentum, unbiased running variance).  fp64 accumulation of the partials.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int slots, int K,
+                                                          int64_t n, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, float momentum,
+                                                          float* running_mean, float* running_var, float* mean_out,
+                                                          float* invstd_out, float* scale_out, float* shift_out) {
+  __shared__ double sh[2][8][32];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + c;
+  double s = 0.0, q = 0.0;
+  if (k < K)
+    for (int j = g; j < slots; j += 8) {
+      s += (double)partial[(size_t)j * 2 * K + k];
+      q += (double)partial[(size_t)j * 2 * K + K + k];
+    }
+  sh[0][g][c] = s; sh[1][g][c] = q;
+  __syncthreads();
+  if (g == 0 && k < K) {
+    s = 0.0; q = 0.0;
+    for (int j = 0; j < 8; ++j) { s += sh[0][j][c]; q += sh[1][j][c]; }
+    const double mean = s / (double)n;
+    double var = q / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[k] * invstd;
+    mean_out[k] = (float)mean;
+    invstd_out[k] = invstd;
+    scale_out[k] = sc;
+    shift_out[k] = beta[k] - (float)mean * sc;
+    if (running_mean) {
+      const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+      running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * (float)mean;
+      running_var[k] = (1.f - momentum) * running_var[k] + momentum * (float)unbiased;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- forward: affine + ReLU + dropout
+// out = dropout(relu(y*scale + shift)); keep iff philox uniform >= p; kept values scaled by 1/(1-p).
+__global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* __restrict__ Y, float* __restrict__ out,
+                                                                  int64_t n_vec, int nvec_row,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int relu, float p,
+                                                                  uint64_t seed, uint64_t offset,
+                                                                  const int32_t* __restrict__ step_dev,
+                                                                  uint64_t step_mul) {
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (step_dev) offset += (uint64_t)(*step_dev) * step_mul;  // graph-replayable per-step offset
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % nvec_row);
+    float4 y = ld4s(Y + 4 * i);
+    if (scale) {
+      const float4 sc = ld4(scale + 4 * cv), sh = ld4(shift + 4 * cv);
+      y.x = fmaf(y.x, sc.x, sh.x); y.y = fmaf(y.y, sc.y, sh.y);
+      y.z = fmaf(y.z, sc.z, sh.z); y.w = fmaf(y.w, sc.w, sh.w);
+    }
+    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    if (p > 0.f) {
+      const uint4 r = philox4x32(seed, offset, (uint64_t)i);
+      y.x = (u32_to_unit(r.x) >= p) ? y.x * inv_keep : 0.f;
+      y.y = (u32_to_unit(r.y) >= p) ? y.y * inv_keep : 0.f;
+      y.z = (u32_to_unit(r.z) >= p) ? y.z * inv_keep : 0.f;
+      y.w = (u32_to_unit(r.w) >= p) ? y.w * inv_keep : 0.f;
+    }
+    st4(out + 4 * i, y);
+  }
+}
+
+// The keep-mask the kernel above uses, materialised (tests inject it into the CPU oracle).
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n_vec, float p,
+                                                           uint64_t seed, uint64_t offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32(seed, offset, (uint64_t)i);
+    uchar4 m;
+    m.x = u32_to_unit(r.x) >= p; m.y = u32_to_unit(r.y) >= p; m.z = u32_to_unit(r.z) >= p; m.w = u32_to_unit(r.w) >= p;
+    reinterpret_cast<uchar4*>(mask)[i] = m;
+  }
+}
+
+// ---------------------------------------------------------------- backward of BN(train)+ReLU+dropout
+// dz = dOut * [Xout > 0] / (1-p)       (Xout>0  <=>  kept by dropout AND relu-active)
+// pass 1: partial column sums of dz and dz*xhat, xhat = (Y-mean)*invstd
+__global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_reduce_kernel(
+    const float* __restrict__ dOut, const float* __restrict__ Xout, const float* __restrict__ Y,
+    const float* __restrict__ mean, const float* __restrict__ invstd, int64_t n_rows, int K, float inv_keep,
+    float* __restrict__ partial, int slots) {
+  extern __shared__ float smem[];
+  const RowMap m = make_row_map(K);
+  const int64_t per = (n_rows + slots - 1) / slots;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n_rows, r0 + per);
+  float4 s = make_float4(0, 0, 0, 0), q = s;
+  if (m.active) {
+    const float4 mu = ld4(mean + 4 * m.cv), is = ld4(invstd + 4 * m.cv);
+    for (int64_t r = r0 + m.rg; r < r1; r += m.rows_per_iter) {
+      const size_t o = (size_t)r * K + 4 * m.cv;
+      const float4 g = ld4(dOut + o), x = ld4(Xout + o), y = ld4(Y + o);
+      const float dx = x.x > 0.f ? g.x * inv_keep : 0.f, dy = x.y > 0.f ? g.y * inv_keep : 0.f;
+      const float dz = x.z > 0.f ? g.z * inv_keep : 0.f, dw = x.w > 0.f ? g.w * inv_keep : 0.f;
+      s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+      q.x = fmaf(dx, (y.x - mu.x) * is.x, q.x); q.y = fmaf(dy, (y.y - mu.y) * is.y, q.y);
+      q.z = fmaf(dz, (y.z - mu.z) * is.z, q.z); q.w = fmaf(dw, (y.w - mu.w) * is.w, q.w);
+    }
+  }
+  reduce_store_2xK(m, K, s, q, smem, partial + (size_t)blockIdx.x * 2 * K);
+}
+
+// partials -> dgamma, dbeta, and the per-column coefficients of pass 2.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int slots, int K,
+                                                              int64_t n, const float* __restrict__ gamma,
+                                                              const float* __restrict__ invstd, float* dgamma,
+                                                              float* dbeta, float* coef /*[3][K]*/) {
+  __shared__ double sh[2][8][32];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + c;
+  double s = 0.0, q = 0.0;
+  if (k < K)
+    for (int j = g; j < slots; j += 8) {
+      s += (double)partial[(size_t)j * 2 * K + k];
+      q += (double)partial[(size_t)j * 2 * K + K + k];
+    }
+  sh[0][g][c] = s; sh[1][g][c] = q;
+  __syncthreads();
+  if (g == 0 && k < K) {
+    s = 0.0; q = 0.0;
+    for (int j = 0; j < 8; ++j) { s += sh[0][j][c]; q += sh[1][j][c]; }
+    dbeta[k] = (float)s;
+    dgamma[k] = (float)q;
+    coef[k] = gamma[k] * invstd[k];
+    coef[K + k] = (float)(s / (double)n);
+    coef[2 * K + k] = (float)(q / (double)n);
+  }
+}
+
+// pass 2: dY = gamma*invstd * (dz - mean(dz) - xhat*mean(dz*xhat)); optional partial column sums of dY
+// (gradient of the conv bias in front of the BatchNorm).
+__global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_apply_kernel(
+    const float* __restrict__ dOut, const float* __restrict__ Xout, const float* __restrict__ Y,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef, int64_t n_rows,
+    int K, float inv_keep, float* __restrict__ dY, float* __restrict__ colsum_partial, int slots) {
+  extern __shared__ float smem[];
+  const RowMap m = make_row_map(K);
+  const int64_t per = (n_rows + slots - 1) / slots;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n_rows, r0 + per);
+  float4 s = make_float4(0, 0, 0, 0), q = s;
+  if (m.active) {
+    const float4 mu = ld4(mean + 4 * m.cv), is = ld4(invstd + 4 * m.cv);
+    const float4 c1 = ld4(coef + 4 * m.cv), c2 = ld4(coef + K + 4 * m.cv), c3 = ld4(coef + 2 * K + 4 * m.cv);
+    for (int64_t r = r0 + m.rg; r < r1; r += m.rows_per_iter) {
+      const size_t o = (size_t)r * K + 4 * m.cv;
+      const float4 g = ld4s(dOut + o), x = ld4s(Xout + o), y = ld4s(Y + o);
+      float4 d;
+      d.x = c1.x * ((x.x > 0.f ? g.x * inv_keep : 0.f) - c2.x - (y.x - mu.x) * is.x * c3.x);
+      d.y = c1.y * ((x.y > 0.f ? g.y * inv_keep : 0.f) - c2.y - (y.y - mu.y) * is.y * c3.y);
+      d.z = c1.z * ((x.z > 0.f ? g.z * inv_keep : 0.f) - c2.z - (y.z - mu.z) * is.z * c3.z);
+      d.w = c1.w * ((x.w > 0.f ? g.w * inv_keep : 0.f) - c2.w - (y.w - mu.w) * is.w * c3.w);
+      st4(dY + o, d);
+      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    }
+  }
+  if (colsum_partial) reduce_store_2xK(m, K, s, q, smem, colsum_partial + (size_t)blockIdx.x * 2 * K);
+}
+
+// Sum partial[slots][2][K] (first plane only) -> out[K]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int slots, int K,
+                                                              float* __restrict__ out) {
+  __shared__ double sh[8][32];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + c;
+  double s = 0.0;
+  if (k < K)
+    for (int j = g; j < slots; j += 8) s += (double)partial[(size_t)j * 2 * K + k];
+  sh[g][c] = s;
+  __syncthreads();
+  if (g == 0 && k < K) {
+    s = 0.0;
+    for (int j = 0; j < 8; ++j) s += sh[j][c];
+    out[k] = (float)s;
+  }
+}
+
+// ---------------------------------------------------------------- Adam (torch.optim.Adam defaults, no amsgrad/decay)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                   float b1, float b2, float eps, const int32_t* __restrict__ step) {
+  const float t = (float)(*step + 1);
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+__global__ void adam_tick_kernel(int32_t* step) { *step += 1; }
+
+static inline int grid_for(int64_t n_items, int per_cta, int cap = 148 * 8) {
+  int64_t g = (n_items + per_cta - 1) / per_cta;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b200gnn
+
+using namespace b200gnn;
+
+static bool rows_ok(int64_t n_rows, int64_t K) { return n_rows >= 0 && K > 0 && K % 4 == 0 && K <= 1024; }
+
+extern "C" int64_t b200gnn_rows_slots(int64_t n_rows) {
+  // one slot per CTA; ~2 CTAs per SM keeps the partial buffer small and the reduction order fixed
+  int64_t s = (n_rows + 255) / 256;
+  if (s > 148 * 4) s = 148 * 4;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" int b200gnn_col_stats_f32(const float* Y, int64_t n_rows, int64_t K, float* partial, int64_t slots,
+                                     void* stream) {
+  if (!rows_ok(n_rows, K) || !Y || !partial || slots < 1 || !aligned_to(Y, 16)) return B200GNN_ERR_BAD_ARG;
+  col_stats4_kernel<<<(int)slots, ROWS_THREADS, 2 * K * sizeof(float), (cudaStream_t)stream>>>(Y, n_rows, (int)K, partial,
+                                                                                             (int)slots);
+  return check_launch();
+}
+
+extern "C" int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int64_t K, int64_t n_rows,
+                                       const float* gamma, const float* beta, float eps, float momentum,
+                                       float* running_mean, float* running_var, float* mean_out, float* invstd_out,
+                                       float* scale_out, float* shift_out, void* stream) {
+  if (!partial || slots < 1 || K <= 0 || n_rows <= 0 || !gamma || !beta || !mean_out || !invstd_out || !scale_out ||
+      !shift_out || ((running_mean == nullptr) != (running_var == nullptr)))
+    return B200GNN_ERR_BAD_ARG;
+  bn_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+      partial, (int)slots, (int)K, n_rows, gamma, beta, eps, momentum, running_mean, running_var, mean_out, invstd_out,
+      scale_out, shift_out);
+  return check_launch();
+}
+
+extern "C" int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                               const float* scale, const float* shift, int relu, float p, uint64_t seed,
+                                               uint64_t offset, const int32_t* step_dev, uint64_t step_mul,
+                                               void* stream) {
+  if (!rows_ok(n_rows, K) || !Y || !out || p < 0.f || p >= 1.f || ((scale == nullptr) != (shift == nullptr)) ||
+      !aligned_to(Y, 16) || !aligned_to(out, 16))
+    return B200GNN_ERR_BAD_ARG;
+  if (n_rows == 0) return B200GNN_OK;
+  const int64_t n_vec = n_rows * (K / 4);
+  affine_relu_dropout_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, seed, offset, step_dev, step_mul);
+  return check_launch();
+}
+
+extern "C" int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p, uint64_t seed,
+                                       uint64_t offset, void* stream) {
+  if (!rows_ok(n_rows, K) || !mask || p < 0.f || p >= 1.f) return B200GNN_ERR_BAD_ARG;
+  if (n_rows == 0) return B200GNN_OK;
+  const int64_t n_vec = n_rows * (K / 4);
+  dropout_mask_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(mask, n_vec, p, seed, offset);
+  return check_launch();
+}
+
+extern "C" int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
+                                      const float* invstd, const float* gamma, int64_t n_rows, int64_t K, float p,
+                                      float* dY, float* dgamma, float* dbeta, float* dbias, float* partial,
+                                      int64_t slots, float* coef, void* stream) {
+  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Xout || !Y || !mean || !invstd || !gamma || !dY || !dgamma ||
+      !dbeta || !partial || !coef || slots < 1 || p < 0.f || p >= 1.f)
+    return B200GNN_ERR_BAD_ARG;
+  if (ROWS_THREADS / (K / 4) < 1) return B200GNN_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const size_t smem = 2 * K * sizeof(float);
+  int rc;
+  bn_act_bwd_reduce_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, n_rows, (int)K, inv_keep,
+                                                                  partial, (int)slots);
+  if ((rc = check_launch())) return rc;
+  bn_bwd_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, n_rows, gamma, invstd, dgamma,
+                                                              dbeta, coef);
+  if ((rc = check_launch())) return rc;
+  bn_act_bwd_apply_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, coef, n_rows, (int)K,
+                                                                 inv_keep, dY, dbias ? partial : nullptr, (int)slots);
+  if ((rc = check_launch())) return rc;
+  if (dbias) {
+    colsum_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, dbias);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}
+
+extern "C" int b200gnn_col_sum_f32(const float* Y, int64_t n_rows, int64_t K, float* out, float* partial,
+                                   int64_t slots, void* stream) {
+  if (!rows_ok(n_rows, K) || !Y || !out || !partial || slots < 1) return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  col_stats4_kernel<<<(int)slots, ROWS_THREADS, 2 * K * sizeof(float), st>>>(Y, n_rows, (int)K, partial, (int)slots);
+  if ((rc = check_launch())) return rc;
+  colsum_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, out);
+  return check_launch();
+}
+
+extern "C" int b200gnn_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                     float lr, float beta1, float beta2, float eps, int32_t* step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step || n < 0) return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (n > 0) {
+    adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step);
+    if ((rc = check_launch())) return rc;
+  }
+  adam_tick_kernel<<<1, 1, 0, st>>>(step);
+  return check_launch();
+}

@@ -5,7 +5,9 @@
 // 79,84; mag_pyg/gnn.py:162) and their backward (same kernel on the CSC view).
 //
 // Design (HBM/L2-bound gather, no tensor cores):
-//   * one warp per destination row; 32 (col,val) pairs are fetched with one
+//   * one warp per CHUNK of consecutive destination rows holding ~chunk_nnz
+//     non-zeros (plan built once per graph), so warps are load-balanced on
+//     power-law graphs; within a row 32 (col,val) pairs are fetched with one
 //     coalesced load and broadcast by warp shuffle; each neighbour's feature
 //     row is gathered with 128-bit read-only loads, U*CH of them in flight per
 //     lane (8 x 16 B) so a warp keeps 4 KB of gather traffic outstanding;
@@ -22,8 +24,6 @@ namespace b200gnn {
 
 constexpr int SPMM_THREADS = 256;
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
-constexpr int SPMM_ROWS_PER_WARP = 8;
-constexpr int SPMM_ROWS_PER_CTA = SPMM_WARPS * SPMM_ROWS_PER_WARP;
 constexpr int SPMM_MAX_SLAB_FLOATS = 512;  // 32 lanes * CH(<=4) * W(<=4)
 
 struct SpmmParams {
@@ -34,12 +34,13 @@ struct SpmmParams {
   float* Y;
   const float* bias;
   float* stat_partial;
+  const int32_t* chunk_rowptr;
   const int32_t* hub_rows;
   const int32_t* hub_segptr;
   float* hub_ws;
   int64_t ldx, ldy;  // in floats
   int32_t n_rows, K, nvec;
-  int32_t hub_threshold, seg_len, n_hub;
+  int32_t hub_threshold, seg_len, n_hub, n_chunks;
   int32_t mean, stream_store, main_grid;
 };
 
@@ -156,11 +157,15 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmPa
 #pragma unroll
   for (int j = 0; j < CH; ++j) { vzero(ssum[j]); vzero(ssq[j]); }
 
-  for (int rr = 0; rr < SPMM_ROWS_PER_WARP; ++rr) {
-    const int64_t row64 = (int64_t)blockIdx.x * SPMM_ROWS_PER_CTA + rr * SPMM_WARPS + warp;
-    if (row64 >= p.n_rows) break;
-    const int row = (int)row64;
-    const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+  // one warp per chunk: a run of consecutive rows holding ~chunk_nnz non-zeros (plan from csr_chunk_plan),
+  // so every warp has about the same amount of gather work whatever the degree distribution.
+  const int chunk = blockIdx.x * SPMM_WARPS + warp;
+  const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
+  const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
+  int end = row_lo < row_hi ? __ldg(p.rowptr + row_lo) : 0;
+  for (int row = row_lo; row < row_hi; ++row) {
+    const int beg = end;
+    end = __ldg(p.rowptr + row + 1);
     const int deg = end - beg;
     if (deg > p.hub_threshold) continue;  // split path owns this row (incl. its statistics)
     for (int slab = 0; slab < nslab; ++slab) {
@@ -402,9 +407,42 @@ __global__ void __launch_bounds__(1024) hub_fill_kernel(const int32_t* __restric
   if (threadIdx.x == 0) hub_segptr[n_hub] = s_base[1];
 }
 
+// chunk c starts at the first row r with key(r) = rowptr[r] + r*row_cost >= c*chunk_nnz  (key is strictly
+// increasing, so empty rows are spread over chunks too); chunk_rowptr[n_chunks] = n_rows.
+__global__ void __launch_bounds__(256) chunk_plan_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
+                                                         int32_t chunk_nnz, int32_t row_cost,
+                                                         int32_t* __restrict__ chunk_rowptr, int64_t n_chunks) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_chunks) return;
+  if (c == n_chunks) { chunk_rowptr[c] = (int32_t)n_rows; return; }
+  const int64_t target = c * (int64_t)chunk_nnz;
+  int64_t lo = 0, hi = n_rows;  // smallest r in [0,n_rows] with key(r) >= target
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t key = (int64_t)rowptr[mid] + mid * (int64_t)row_cost;
+    if (key >= target) hi = mid; else lo = mid + 1;
+  }
+  chunk_rowptr[c] = (int32_t)lo;
+}
+
 }  // namespace b200gnn
 
 using namespace b200gnn;
+
+extern "C" int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz, int32_t row_cost) {
+  if (n_rows < 0 || nnz < 0 || chunk_nnz <= 0 || row_cost <= 0) return B200GNN_ERR_BAD_ARG;
+  const int64_t total = nnz + n_rows * (int64_t)row_cost;
+  return total == 0 ? 0 : (total + chunk_nnz - 1) / chunk_nnz;
+}
+
+extern "C" int b200gnn_csr_chunk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t chunk_nnz,
+                                      int32_t row_cost, int32_t* chunk_rowptr, void* stream) {
+  const int64_t n_chunks = b200gnn_csr_chunk_count(n_rows, nnz, chunk_nnz, row_cost);
+  if (n_chunks < 0 || !rowptr || !chunk_rowptr) return B200GNN_ERR_BAD_ARG;
+  chunk_plan_kernel<<<(int)((n_chunks + 1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, n_rows, chunk_nnz,
+                                                                                        row_cost, chunk_rowptr, n_chunks);
+  return check_launch();
+}
 
 extern "C" int b200gnn_csr_hub_count(const int32_t* rowptr, int64_t n_rows, int32_t hub_threshold, int32_t seg_len,
                                      int32_t* counts_out, void* stream) {
@@ -421,21 +459,22 @@ extern "C" int b200gnn_csr_hub_fill(const int32_t* rowptr, int64_t n_rows, int32
   return check_launch();
 }
 
-extern "C" int64_t b200gnn_spmm_stat_slots(int64_t n_rows, int64_t n_hub) {
-  return (n_rows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA + n_hub;
+extern "C" int64_t b200gnn_spmm_stat_slots(int64_t n_chunks, int64_t n_hub) {
+  return (n_chunks + SPMM_WARPS - 1) / SPMM_WARPS + n_hub;
 }
 
 extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
                                     int64_t ldx, float* Y, int64_t ldy, int64_t n_rows, int64_t n_src, int64_t K,
-                                    int reduce, const float* bias, float* stat_partial, int32_t hub_threshold,
+                                    int reduce, const float* bias, float* stat_partial,
+                                    const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
                                     int32_t seg_len, const int32_t* hub_rows, const int32_t* hub_segptr,
                                     int64_t n_hub, int64_t n_seg, float* hub_workspace, void* stream) {
   if (n_rows < 0 || n_src < 0 || K <= 0 || n_rows >= INT32_MAX || n_src >= INT32_MAX || K > (1 << 20))
     return B200GNN_ERR_BAD_ARG;
   if (reduce != B200GNN_REDUCE_SUM && reduce != B200GNN_REDUCE_MEAN) return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
-  if (!rowptr || !Y || ldy < K) return B200GNN_ERR_BAD_ARG;
-  if (n_src > 0 && (!X || !col || ldx < K)) return B200GNN_ERR_BAD_ARG;
+  if (!rowptr || !Y || ldy < K || !chunk_rowptr || n_chunks <= 0 || n_chunks >= INT32_MAX) return B200GNN_ERR_BAD_ARG;
+  if (n_src > 0 && (!X || ldx < K)) return B200GNN_ERR_BAD_ARG;  // col may be NULL when nnz == 0
   if (n_hub < 0 || n_seg < 0 || hub_threshold < 0) return B200GNN_ERR_BAD_ARG;
   if (n_hub > 0 && (!hub_rows || !hub_segptr || !hub_workspace || seg_len <= 0 || n_seg < n_hub))
     return B200GNN_ERR_BAD_ARG;
@@ -444,13 +483,14 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   SpmmParams p;
   p.rowptr = rowptr; p.col = col; p.val = val; p.X = X; p.Y = Y; p.bias = bias;
   p.stat_partial = stat_partial;
+  p.chunk_rowptr = chunk_rowptr; p.n_chunks = (int32_t)n_chunks;
   p.hub_rows = hub_rows; p.hub_segptr = hub_segptr; p.hub_ws = hub_workspace;
   p.ldx = ldx; p.ldy = ldy;
   p.n_rows = (int32_t)n_rows; p.K = (int32_t)K;
   p.hub_threshold = hub_threshold; p.seg_len = seg_len; p.n_hub = (int32_t)n_hub;
   p.mean = reduce == B200GNN_REDUCE_MEAN;
   p.stream_store = (n_rows * K * 4 > (int64_t)64 << 20) ? 1 : 0;
-  p.main_grid = (int32_t)((n_rows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA);
+  p.main_grid = (int32_t)((n_chunks + SPMM_WARPS - 1) / SPMM_WARPS);
 
   // widest vector type the layout allows
   int W = 1;
@@ -469,7 +509,7 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   if (rc) return rc;
 
   if (fused_stats && !single_slab) {
-    const int slots = (int)b200gnn_spmm_stat_slots(n_rows, n_hub);
+    const int slots = (int)b200gnn_spmm_stat_slots(n_chunks, n_hub);
     col_stats_kernel<<<slots, 256, 0, st>>>(Y, ldy, n_rows, (int)K, fused_stats, slots);
     if ((rc = check_launch())) return rc;
   }

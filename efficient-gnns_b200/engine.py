@@ -1,0 +1,259 @@
+"""Fused full-batch training step for the GCN student (+ logit-KD) — BASELINE.json configs[1].
+
+Mirrors what one call of the reference's ``train()`` does for ``--gnn gcn --training kd|supervised``
+(arxiv_pyg/gnn.py:102-195 with ``GCN.forward`` :45-53, ``kd_criterion`` criterion.py:8-21, Adam :308-315):
+
+    for each layer:  H = X W            (dense GEMM; cuBLAS fp32 through torch.mm — a plain library GEMM)
+                     Y = Â H + b        (b200gnn SpMM, bias + BatchNorm statistics fused in the epilogue)
+                     X = dropout(relu(BN(Y)))   (one b200gnn pass)
+    loss, dlogits = fused CE/KD row kernel over logits[train_idx]
+    backward: dH = Âᵀ dY (same SpMM kernel), dW = Xᵀ dH, dX = dH Wᵀ, fused BN/ReLU/dropout backward
+    Adam over one flat parameter buffer.
+
+No autograd tape: activations live in preallocated buffers and the whole step (≈40 launches) is captured
+into one CUDA graph.  Everything except the three GEMM shapes is hand-written sm_100a code behind the C ABI.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib, ops
+from .sparse import CsrGraph, SparseTensor
+
+
+def gcn_norm(adj: SparseTensor) -> SparseTensor:
+    """PyG gcn_norm for a SparseTensor: Â = D^-1/2 (A + I) D^-1/2, A value-less => ones."""
+    if not adj.has_value():
+        adj = adj.fill_value(1.0)
+    adj = adj.fill_diag(1.0)
+    deg = adj.sum(dim=1)
+    dis = deg.pow(-0.5)
+    dis.masked_fill_(dis == float("inf"), 0.0)
+    row, col, val = adj.coo()
+    return adj.set_value(dis[row] * val * dis[col])
+
+
+def _is_symmetric(adj: SparseTensor) -> bool:
+    st = adj.storage
+    if st.sparse_sizes()[0] != st.sparse_sizes()[1]:
+        return False
+    perm = st.csr2csc()
+    same = torch.equal(st.col()[perm], st.row()) and torch.equal(st.row()[perm], st.col())
+    if same and st.value() is not None:
+        same = torch.equal(st.value()[perm], st.value())
+    return bool(same)
+
+
+class GCNStudentTrainer:
+    """State + fused step of an L-layer GCN student on one GPU."""
+
+    def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
+                 alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+        assert adj.is_cuda(), "the engine runs on a CUDA device"
+        self.device = adj.device
+        self.dims, self.L = list(dims), len(dims) - 1
+        self.p, self.lr, self.alpha, self.kd_T = float(dropout), float(lr), float(alpha), float(kd_T)
+        self.bn_eps, self.bn_momentum = bn_eps, bn_momentum
+        self.seed = int(seed)
+        for d in dims[1:]:
+            assert d % 4 == 0 and d <= 1024, "layer widths must be multiples of 4 (128-bit rows)"
+        self.N = adj.size(0)
+
+        norm = gcn_norm(adj)                     # cached=True semantics: normalise once (arxiv_pyg/gnn.py:28)
+        self.G: CsrGraph = norm.storage.engine_csr()
+        self.Gt: CsrGraph = self.G if _is_symmetric(norm) else norm.storage.engine_csc("value")
+        self.nnz = self.G.nnz
+
+        # ---- flat parameters: per layer W [in,out], b [out]; per hidden layer gamma, beta
+        sizes = []
+        for l in range(self.L):
+            sizes += [dims[l] * dims[l + 1], dims[l + 1]]
+            if l < self.L - 1:
+                sizes += [dims[l + 1], dims[l + 1]]
+        n_par = sum(sizes)
+        dev = self.device
+        self.params = torch.zeros(n_par, device=dev)
+        self.grads = torch.zeros(n_par, device=dev)
+        self.exp_avg = torch.zeros(n_par, device=dev)
+        self.exp_avg_sq = torch.zeros(n_par, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.W, self.b, self.gamma, self.beta = [], [], [], []
+        self.gW, self.gb, self.ggamma, self.gbeta = [], [], [], []
+        off = 0
+
+        def take(n, shape):
+            nonlocal off
+            v = (self.params[off:off + n].view(shape), self.grads[off:off + n].view(shape))
+            off += n
+            return v
+        for l in range(self.L):
+            w, gw = take(dims[l] * dims[l + 1], (dims[l], dims[l + 1]))
+            b, gb = take(dims[l + 1], (dims[l + 1],))
+            self.W.append(w); self.gW.append(gw); self.b.append(b); self.gb.append(gb)
+            if l < self.L - 1:
+                g, gg = take(dims[l + 1], (dims[l + 1],))
+                be, gbe = take(dims[l + 1], (dims[l + 1],))
+                self.gamma.append(g); self.ggamma.append(gg); self.beta.append(be); self.gbeta.append(gbe)
+        self.running_mean = [torch.zeros(d, device=dev) for d in dims[1:-1]]
+        self.running_var = [torch.ones(d, device=dev) for d in dims[1:-1]]
+        self.reset_parameters(seed)
+
+        # ---- activations / gradients (preallocated; CUDA-graph friendly)
+        N = self.N
+        buf = lambda k: torch.empty(N, k, device=dev)  # noqa: E731
+        self.H = [buf(dims[l + 1]) for l in range(self.L)]            # X W
+        self.Y = [buf(dims[l + 1]) for l in range(self.L)]            # Â H + b  (last = logits)
+        self.A = [buf(dims[l + 1]) for l in range(self.L - 1)]        # dropout(relu(BN(Y)))
+        self.dY = [buf(dims[l + 1]) for l in range(self.L)]
+        self.dH = [buf(dims[l + 1]) for l in range(self.L)]
+        self.dA = [buf(dims[l + 1]) for l in range(self.L - 1)]
+        slots_spmm = ops.stat_slots(self.G)
+        self.stat_part = [torch.empty(slots_spmm, 2, dims[l + 1], device=dev) for l in range(self.L - 1)]
+        self.bn = [torch.empty(4, dims[l + 1], device=dev) for l in range(self.L - 1)]   # mean, invstd, scale, shift
+        self.rs = ops.rows_slots(N)
+        self.loss_out = torch.zeros(3, device=dev)
+        self.kd_part = torch.empty(2 * int(lib.load().b200gnn_kd_partials(N)), device=dev)
+        self._graph = None
+        self._static: Dict[str, torch.Tensor] = {}
+        for k in set(dims[1:]):
+            self._part(k); self._coef(k)
+
+    # ------------------------------------------------------------------ parameters
+    def reset_parameters(self, seed: int = 0):
+        """GCNConv: glorot weight, zero bias; BatchNorm1d: ones / zeros."""
+        g = torch.Generator().manual_seed(seed)
+        for l in range(self.L):
+            fan_in, fan_out = self.dims[l], self.dims[l + 1]
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            self.W[l].copy_((torch.rand(fan_in, fan_out, generator=g) * 2 - 1) * a)
+            self.b[l].zero_()
+        for l in range(self.L - 1):
+            self.gamma[l].fill_(1.0); self.beta[l].zero_()
+            self.running_mean[l].zero_(); self.running_var[l].fill_(1.0)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Keys of the reference's GCN module under PyG 1.x (convs.i.weight / bias, bns.i.*)."""
+        sd = {}
+        for l in range(self.L):
+            sd[f"convs.{l}.weight"] = self.W[l].detach().clone()
+            sd[f"convs.{l}.bias"] = self.b[l].detach().clone()
+        for l in range(self.L - 1):
+            sd[f"bns.{l}.weight"] = self.gamma[l].detach().clone()
+            sd[f"bns.{l}.bias"] = self.beta[l].detach().clone()
+            sd[f"bns.{l}.running_mean"] = self.running_mean[l].clone()
+            sd[f"bns.{l}.running_var"] = self.running_var[l].clone()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        for l in range(self.L):
+            self.W[l].copy_(sd[f"convs.{l}.weight"]); self.b[l].copy_(sd[f"convs.{l}.bias"])
+        for l in range(self.L - 1):
+            self.gamma[l].copy_(sd[f"bns.{l}.weight"]); self.beta[l].copy_(sd[f"bns.{l}.bias"])
+            if f"bns.{l}.running_mean" in sd:
+                self.running_mean[l].copy_(sd[f"bns.{l}.running_mean"]); self.running_var[l].copy_(sd[f"bns.{l}.running_var"])
+
+    # ------------------------------------------------------------------ forward / backward
+    def dropout_offset(self, layer: int, step: int) -> int:
+        return layer + step * self.L
+
+    def forward(self, x: torch.Tensor, training: bool = True) -> torch.Tensor:
+        """Returns logits [N,C]; hidden activations stay in self.A (self.A[-1] is the reference's model.out_feat)."""
+        inp = x
+        for l in range(self.L):
+            torch.mm(inp, self.W[l], out=self.H[l])
+            last = l == self.L - 1
+            if last:
+                ops.spmm_csr(self.G, self.H[l], "sum", bias=self.b[l], out=self.Y[l])
+            elif training:
+                ops.spmm_csr(self.G, self.H[l], "sum", bias=self.b[l], out=self.Y[l], stat_partial=self.stat_part[l])
+                ops.bn_finalize(self.stat_part[l], self.N, self.gamma[l], self.beta[l], self.bn_eps, self.bn_momentum,
+                                self.running_mean[l], self.running_var[l], out=self.bn[l])
+                ops.affine_relu_dropout(self.Y[l], self.bn[l][2], self.bn[l][3], True, self.p, self.seed, l,
+                                        out=self.A[l], step_dev=self.step_count, step_mul=self.L)
+                inp = self.A[l]
+            else:
+                ops.spmm_csr(self.G, self.H[l], "sum", bias=self.b[l], out=self.Y[l])
+                scale = self.gamma[l] * torch.rsqrt(self.running_var[l] + self.bn_eps)
+                shift = self.beta[l] - self.running_mean[l] * scale
+                ops.affine_relu_dropout(self.Y[l], scale, shift, True, 0.0, out=self.A[l])
+                inp = self.A[l]
+        return self.Y[-1]
+
+    def backward(self, x: torch.Tensor):
+        """Consumes self.dY[-1] (d loss / d logits); fills self.grads."""
+        for l in range(self.L - 1, -1, -1):
+            inp = x if l == 0 else self.A[l - 1]
+            if l == self.L - 1:
+                ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(self.dims[l + 1]))
+            ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
+            torch.mm(inp.t(), self.dH[l], out=self.gW[l])
+            if l > 0:
+                torch.mm(self.dH[l], self.W[l].t(), out=self.dA[l - 1])
+                k = self.dims[l]
+                part = self._part(k)
+                ops.bn_act_bwd(self.dA[l - 1], self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
+                               self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
+                               d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
+
+    def _part(self, k: int) -> torch.Tensor:
+        key = f"part{k}"
+        if key not in self._static:
+            self._static[key] = torch.empty(self.rs, 2, k, device=self.device)
+        return self._static[key]
+
+    def _coef(self, k: int) -> torch.Tensor:
+        key = f"coef{k}"
+        if key not in self._static:
+            self._static[key] = torch.empty(3, k, device=self.device)
+        return self._static[key]
+
+    def _step_impl(self, x, y, train_idx, teacher_logits):
+        logits = self.forward(x, training=True)
+        self.dY[-1].zero_()
+        ops.kd_loss_fwd_bwd(logits, y, train_idx, teacher_logits, self.alpha, self.kd_T, d_logits=self.dY[-1],
+                            loss_out=self.loss_out, partial=self.kd_part)
+        self.backward(x)
+        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr)
+
+    def train_step(self, x, y, train_idx, teacher_logits=None) -> torch.Tensor:
+        """One reference ``train()`` call (kd if teacher_logits is given, else supervised).
+        Returns the device tensor [loss, loss_cls, loss_kd] (no host sync)."""
+        self._step_impl(x, y, train_idx, teacher_logits)
+        return self.loss_out
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, x, y, train_idx, teacher_logits=None, warmup: int = 2):
+        """Capture the step on static input buffers; afterwards ``replay()`` runs one full step."""
+        self._static.update(x=x, y=y, train_idx=train_idx, teacher=teacher_logits)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_impl(x, y, train_idx, teacher_logits)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._step_impl(x, y, train_idx, teacher_logits)
+        return self
+
+    def replay(self) -> torch.Tensor:
+        self._graph.replay()
+        return self.loss_out
+
+    # ------------------------------------------------------------------ accounting
+    def launches_per_step(self) -> int:
+        """b200gnn kernel launches in one training step (counted, not estimated)."""
+        before = lib.launch_count()
+        st = self._static
+        self._step_impl(st["x"], st["y"], st["train_idx"], st["teacher"])
+        return lib.launch_count() - before
+
+    def spmm_algorithmic_bytes(self) -> Dict[int, int]:
+        """Compulsory HBM bytes of one aggregation per feature width:
+        2*N*K*4 (read X, write Y) + nnz*(4 col + 4 val) + (N+1)*4."""
+        return {k: 2 * self.N * k * 4 + self.nnz * 8 + (self.N + 1) * 4 for k in set(self.dims[1:])}

@@ -33,11 +33,27 @@ SIGNATURES = {
     "b200gnn_last_cuda_error": (C.c_char_p, []),
     "b200gnn_launch_count": (_i64, []),
     "b200gnn_reset_launch_count": (None, []),
+    "b200gnn_csr_chunk_count": (_i64, [_i64, _i64, _i32, _i32]),
+    "b200gnn_csr_chunk_plan": (_int, [_i32p, _i64, _i64, _i32, _i32, _i32p, _ptr]),
     "b200gnn_csr_hub_count": (_int, [_i32p, _i64, _i32, _i32, _i32p, _ptr]),
     "b200gnn_csr_hub_fill": (_int, [_i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _ptr]),
     "b200gnn_spmm_stat_slots": (_i64, [_i64, _i64]),
     "b200gnn_spmm_csr_f32": (_int, [_i32p, _i32p, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _int,
-                                    _f32p, _f32p, _i32, _i32, _i32p, _i32p, _i64, _i64, _f32p, _ptr]),
+                                    _f32p, _f32p, _i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _i64, _f32p, _ptr]),
+    "b200gnn_rows_slots": (_i64, [_i64]),
+    "b200gnn_col_stats_f32": (_int, [_f32p, _i64, _i64, _f32p, _i64, _ptr]),
+    "b200gnn_col_sum_f32": (_int, [_f32p, _i64, _i64, _f32p, _f32p, _i64, _ptr]),
+    "b200gnn_bn_finalize_f32": (_int, [_f32p, _i64, _i64, _i64, _f32p, _f32p, _f32, _f32, _f32p, _f32p,
+                                       _f32p, _f32p, _f32p, _f32p, _ptr]),
+    "b200gnn_affine_relu_dropout_f32": (_int, [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _int, _f32, _u64, _u64,
+                                               _i32p, _u64, _ptr]),
+    "b200gnn_dropout_mask_u8": (_int, [_ptr, _i64, _i64, _f32, _u64, _u64, _ptr]),
+    "b200gnn_bn_act_bwd_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _f32, _f32p, _f32p,
+                                      _f32p, _f32p, _f32p, _i64, _f32p, _ptr]),
+    "b200gnn_adam_step_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f32, _f32, _f32, _f32, _i32p, _ptr]),
+    "b200gnn_kd_partials": (_i64, [_i64]),
+    "b200gnn_kd_loss_fwd_bwd_f32": (_int, [_f32p, _i64, _ptr, _i64, _ptr, _f32p, _i64, _i64, _f32, _f32, _f32p, _i64,
+                                           _f32p, _f32p, _ptr]),
 }
 
 _lib = None

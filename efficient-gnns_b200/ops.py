@@ -16,7 +16,7 @@ _REDUCE = {"sum": lib.REDUCE_SUM, "add": lib.REDUCE_SUM, "mean": lib.REDUCE_MEAN
 
 
 def stat_slots(g: CsrGraph) -> int:
-    return int(lib.load().b200gnn_spmm_stat_slots(g.n_rows, g.n_hub))
+    return int(lib.load().b200gnn_spmm_stat_slots(g.n_chunks, g.n_hub))
 
 
 def spmm_csr(g: CsrGraph, x: torch.Tensor, reduce: str = "sum", bias: Optional[torch.Tensor] = None,
@@ -40,7 +40,7 @@ def spmm_csr(g: CsrGraph, x: torch.Tensor, reduce: str = "sum", bias: Optional[t
         lib.dptr(g.val, torch.float32, "val"), lib.dptr(x, torch.float32, "x"), x.stride(0),
         lib.dptr(out, torch.float32, "out"), out.stride(0), g.n_rows, g.n_cols, K, _REDUCE[reduce],
         lib.dptr(bias, torch.float32, "bias"), lib.dptr(stat_partial, torch.float32, "stat_partial"),
-        g.hub_threshold, g.seg_len,
+        g.chunk_rowptr.data_ptr(), g.n_chunks, g.hub_threshold, g.seg_len,
         g.hub_rows.data_ptr() if g.n_hub else None, g.hub_segptr.data_ptr() if g.n_hub else None,
         g.n_hub, g.n_seg, None if ws is None else ws.data_ptr(), lib.stream_ptr())
     lib.check(rc, "spmm_csr_f32")
@@ -75,3 +75,116 @@ def matmul(adj: SparseTensor, x: torch.Tensor, reduce: str = "sum") -> torch.Ten
     if x.dim() == 1:
         return matmul(adj, x.unsqueeze(-1), reduce).squeeze(-1)
     return _SpMM.apply(x, adj, reduce)
+
+
+# ----------------------------------------------------------------------------- dense row passes (raw launches)
+def _f32(t, name):
+    return lib.dptr(t, torch.float32, name)
+
+
+def rows_slots(n_rows: int) -> int:
+    return int(lib.load().b200gnn_rows_slots(n_rows))
+
+
+def col_stats(y: torch.Tensor, partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """partial[slots][2][K]: per-slot column sums / sums of squares of y [n,K]."""
+    n, K = y.shape
+    slots = rows_slots(n)
+    if partial is None:
+        partial = torch.empty(slots, 2, K, dtype=torch.float32, device=y.device)
+    lib.check(lib.load().b200gnn_col_stats_f32(_f32(y, "y"), n, K, _f32(partial, "partial"), slots, lib.stream_ptr()),
+              "col_stats_f32")
+    return partial
+
+
+def col_sum(y: torch.Tensor, out: Optional[torch.Tensor] = None, partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, K = y.shape
+    slots = rows_slots(n)
+    if out is None:
+        out = torch.empty(K, dtype=torch.float32, device=y.device)
+    if partial is None:
+        partial = torch.empty(slots, 2, K, dtype=torch.float32, device=y.device)
+    lib.check(lib.load().b200gnn_col_sum_f32(_f32(y, "y"), n, K, _f32(out, "out"), _f32(partial, "partial"), slots,
+                                             lib.stream_ptr()), "col_sum_f32")
+    return out
+
+
+def bn_finalize(partial: torch.Tensor, n_rows: int, gamma, beta, eps: float = 1e-5, momentum: float = 0.1,
+                running_mean=None, running_var=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns a [4,K] tensor: rows = mean, invstd, scale, shift."""
+    slots, _, K = partial.shape
+    if out is None:
+        out = torch.empty(4, K, dtype=torch.float32, device=partial.device)
+    lib.check(lib.load().b200gnn_bn_finalize_f32(
+        _f32(partial, "partial"), slots, K, n_rows, _f32(gamma, "gamma"), _f32(beta, "beta"), eps, momentum,
+        _f32(running_mean, "running_mean"), _f32(running_var, "running_var"),
+        out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), lib.stream_ptr()), "bn_finalize_f32")
+    return out
+
+
+def affine_relu_dropout(y: torch.Tensor, scale=None, shift=None, relu: bool = True, p: float = 0.0, seed: int = 0,
+                        offset: int = 0, out: Optional[torch.Tensor] = None, step_dev: Optional[torch.Tensor] = None,
+                        step_mul: int = 0) -> torch.Tensor:
+    n, K = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    lib.check(lib.load().b200gnn_affine_relu_dropout_f32(
+        _f32(y, "y"), _f32(out, "out"), n, K, _f32(scale, "scale"), _f32(shift, "shift"), int(relu), p, seed, offset,
+        lib.dptr(step_dev, torch.int32, "step_dev"), step_mul, lib.stream_ptr()), "affine_relu_dropout_f32")
+    return out
+
+
+def dropout_mask(n_rows: int, K: int, p: float, seed: int, offset: int, device="cuda") -> torch.Tensor:
+    """The keep-mask (uint8 [n,K]) that affine_relu_dropout uses for (seed, offset)."""
+    mask = torch.empty(n_rows, K, dtype=torch.uint8, device=device)
+    lib.check(lib.load().b200gnn_dropout_mask_u8(mask.data_ptr(), n_rows, K, p, seed, offset, lib.stream_ptr()),
+              "dropout_mask_u8")
+    return mask
+
+
+def bn_act_bwd(d_out, x_out, y, mean, invstd, gamma, p: float, d_y=None, d_gamma=None, d_beta=None, d_bias=None,
+               partial=None, coef=None, want_dbias: bool = True):
+    """Backward of x_out = dropout_p(relu(BN_train(y))). Returns (d_y, d_gamma, d_beta, d_bias)."""
+    n, K = y.shape
+    dev = y.device
+    slots = rows_slots(n)
+    d_y = torch.empty_like(y) if d_y is None else d_y
+    d_gamma = torch.empty(K, device=dev) if d_gamma is None else d_gamma
+    d_beta = torch.empty(K, device=dev) if d_beta is None else d_beta
+    if want_dbias and d_bias is None:
+        d_bias = torch.empty(K, device=dev)
+    partial = torch.empty(slots, 2, K, device=dev) if partial is None else partial
+    coef = torch.empty(3, K, device=dev) if coef is None else coef
+    lib.check(lib.load().b200gnn_bn_act_bwd_f32(
+        _f32(d_out, "d_out"), _f32(x_out, "x_out"), _f32(y, "y"), _f32(mean, "mean"), _f32(invstd, "invstd"),
+        _f32(gamma, "gamma"), n, K, p, _f32(d_y, "d_y"), _f32(d_gamma, "d_gamma"), _f32(d_beta, "d_beta"),
+        _f32(d_bias, "d_bias") if want_dbias else None, _f32(partial, "partial"), slots, _f32(coef, "coef"),
+        lib.stream_ptr()), "bn_act_bwd_f32")
+    return d_y, d_gamma, d_beta, d_bias
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
+    lib.check(lib.load().b200gnn_adam_step_f32(
+        _f32(params, "params"), _f32(grads, "grads"), _f32(exp_avg, "exp_avg"), _f32(exp_avg_sq, "exp_avg_sq"),
+        params.numel(), lr, betas[0], betas[1], eps, lib.dptr(step, torch.int32, "step"), lib.stream_ptr()),
+        "adam_step_f32")
+
+
+def kd_loss_fwd_bwd(logits, labels, train_idx, teacher_logits=None, alpha: float = 0.9, T: float = 4.0,
+                    d_logits=None, loss_out=None, partial=None):
+    """Fused CE / logit-KD over rows train_idx of FULL [N,C] matrices; returns (loss_out[3], d_logits [N,C])."""
+    N, C = logits.shape
+    n_train = train_idx.numel() if train_idx is not None else N
+    L = lib.load()
+    if d_logits is None:
+        d_logits = torch.zeros_like(logits)
+    if loss_out is None:
+        loss_out = torch.empty(3, dtype=torch.float32, device=logits.device)
+    if partial is None:
+        partial = torch.empty(2 * int(L.b200gnn_kd_partials(n_train)), dtype=torch.float32, device=logits.device)
+    lib.check(L.b200gnn_kd_loss_fwd_bwd_f32(
+        _f32(logits, "logits"), logits.stride(0), lib.dptr(train_idx, torch.int64, "train_idx"), n_train,
+        lib.dptr(labels, torch.int64, "labels"), _f32(teacher_logits, "teacher_logits"),
+        teacher_logits.stride(0) if teacher_logits is not None else 0, C, alpha, T, _f32(d_logits, "d_logits"),
+        d_logits.stride(0), _f32(loss_out, "loss_out"), _f32(partial, "partial"), lib.stream_ptr()), "kd_loss_fwd_bwd_f32")
+    return loss_out, d_logits

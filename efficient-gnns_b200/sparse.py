@@ -10,15 +10,17 @@ upstream's SparseStorage caches rowptr / colptr / csr2csc / rowcount.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Optional, Tuple
 
 import torch
 
 from . import lib
 
-HUB_THRESHOLD = 512   # rows with more non-zeros than this are split across CTAs
-HUB_SEG_LEN = 512     # non-zeros per hub segment (one CTA each)
+HUB_THRESHOLD = 256   # rows with more non-zeros than this are split across CTAs
+HUB_SEG_LEN = 256     # non-zeros per hub segment (one CTA each)
+CHUNK_NNZ = 128       # non-zeros per warp-sized chunk of consecutive rows
+CHUNK_ROW_COST = 4    # per-row cost (in non-zero equivalents) when cutting chunks
 
 
 def _narrow_i32(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -35,8 +37,12 @@ class CsrGraph:
     val: Optional[torch.Tensor]
     n_rows: int
     n_cols: int
-    hub_threshold: int = HUB_THRESHOLD
-    seg_len: int = HUB_SEG_LEN
+    hub_threshold: int = 0
+    seg_len: int = 0
+    chunk_nnz: int = 0
+    row_cost: int = 0
+    chunk_rowptr: Optional[torch.Tensor] = None
+    n_chunks: int = 0
     hub_rows: Optional[torch.Tensor] = None
     hub_segptr: Optional[torch.Tensor] = None
     n_hub: int = 0
@@ -51,10 +57,23 @@ class CsrGraph:
     def device(self):
         return self.rowptr.device
 
-    def build_hub_plan(self) -> "CsrGraph":
-        """Two C-ABI calls (count, fill) with one host read of the counts in between (one-off per graph)."""
+    def build_plan(self, hub_threshold: Optional[int] = None, seg_len: Optional[int] = None,
+                   chunk_nnz: Optional[int] = None, row_cost: Optional[int] = None) -> "CsrGraph":
+        """Chunk plan (load balance) + hub plan (row splitting): C-ABI calls with one host read of the hub
+        counts in between; one-off per graph, cached with the storage."""
+        self.hub_threshold = HUB_THRESHOLD if hub_threshold is None else hub_threshold
+        self.seg_len = HUB_SEG_LEN if seg_len is None else seg_len
+        self.chunk_nnz = CHUNK_NNZ if chunk_nnz is None else chunk_nnz
+        self.row_cost = CHUNK_ROW_COST if row_cost is None else row_cost
+        self._ws.clear()
         L = lib.load()
         st = lib.stream_ptr()
+        self.n_chunks = int(L.b200gnn_csr_chunk_count(self.n_rows, self.nnz, self.chunk_nnz, self.row_cost))
+        self.chunk_rowptr = torch.zeros(self.n_chunks + 1, dtype=torch.int32, device=self.device)
+        if self.n_rows > 0:
+            lib.check(L.b200gnn_csr_chunk_plan(lib.dptr(self.rowptr, torch.int32, "rowptr"), self.n_rows, self.nnz,
+                                               self.chunk_nnz, self.row_cost, self.chunk_rowptr.data_ptr(), st),
+                      "csr_chunk_plan")
         counts = torch.zeros(2, dtype=torch.int32, device=self.device)
         lib.check(L.b200gnn_csr_hub_count(lib.dptr(self.rowptr, torch.int32, "rowptr"), self.n_rows,
                                           self.hub_threshold, self.seg_len, counts.data_ptr(), st), "csr_hub_count")
@@ -84,7 +103,7 @@ def csr_graph_from(rowptr64: torch.Tensor, col64: torch.Tensor, val: Optional[to
         raise lib.B200GnnError("engine graphs live on a CUDA device; there is no CPU fallback")
     g = CsrGraph(_narrow_i32(rowptr64, "rowptr"), _narrow_i32(col64, "col"),
                  None if val is None else val.to(torch.float32).contiguous(), n_rows, n_cols)
-    return g.build_hub_plan()
+    return g.build_plan()
 
 
 def ind2ptr(ind: torch.Tensor, size: int) -> torch.Tensor:
@@ -162,8 +181,7 @@ class SparseStorage:
         g = self._engine.get("csr_u")
         if g is None:
             base = self.engine_csr()
-            g = CsrGraph(base.rowptr, base.col, None, base.n_rows, base.n_cols, base.hub_threshold, base.seg_len,
-                         base.hub_rows, base.hub_segptr, base.n_hub, base.n_seg)
+            g = replace(base, val=None, _ws={})
             self._engine["csr_u"] = g
         return g
 

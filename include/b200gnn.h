@@ -49,6 +49,21 @@ int64_t b200gnn_launch_count(void);
 void b200gnn_reset_launch_count(void);
 
 /* ------------------------------------------------------------------ *
+ * CSR chunk plan: load balance for power-law graphs.  Chunk c is the run of
+ * consecutive rows starting at the first row r with
+ *     rowptr[r] + r*row_cost >= c*chunk_nnz ,
+ * so each chunk (= one warp of the SpMM kernel) holds about chunk_nnz
+ * non-zeros (+ row_cost per row, which also spreads empty rows).
+ *   n_chunks = b200gnn_csr_chunk_count(...)   (host arithmetic only)
+ *   chunk_rowptr: int32[n_chunks+1], chunk_rowptr[n_chunks] = n_rows
+ * ------------------------------------------------------------------ */
+int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz,
+                                int32_t row_cost);
+int b200gnn_csr_chunk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz,
+                           int32_t chunk_nnz, int32_t row_cost,
+                           int32_t* chunk_rowptr, void* stream);
+
+/* ------------------------------------------------------------------ *
  * CSR hub plan.  Rows whose degree exceeds `hub_threshold` are split into
  * segments of `seg_len` non-zeros processed by whole CTAs, so one hub node
  * (ARXIV-shape: degree ~2e4) cannot serialise a warp.  Built once per graph
@@ -79,20 +94,99 @@ int b200gnn_csr_hub_fill(const int32_t* rowptr, int64_t n_rows,
  *          receives a deterministic partial column sum (slot,0,:) and sum of
  *          squares (slot,1,:) of the rows of Y it produced, for the
  *          BatchNorm1d that follows the conv (arxiv_pyg/gnn.py:48).
+ *   chunk_rowptr/n_chunks : plan from b200gnn_csr_chunk_plan (required).
  *   hub_* : plan from b200gnn_csr_hub_*; n_hub==0 disables the split path
  *          (then hub_threshold must be >= the maximum degree or INT32_MAX).
  *   hub_workspace : float[n_seg][K] scratch for segment partials.
  * MEAN divides by max(degree,1); empty rows give 0 (+bias).
  * ------------------------------------------------------------------ */
-int64_t b200gnn_spmm_stat_slots(int64_t n_rows, int64_t n_hub);
+int64_t b200gnn_spmm_stat_slots(int64_t n_chunks, int64_t n_hub);
 int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col,
                          const float* val, const float* X, int64_t ldx,
                          float* Y, int64_t ldy, int64_t n_rows, int64_t n_src,
                          int64_t K, int reduce, const float* bias,
-                         float* stat_partial, int32_t hub_threshold,
+                         float* stat_partial, const int32_t* chunk_rowptr,
+                         int64_t n_chunks, int32_t hub_threshold,
                          int32_t seg_len, const int32_t* hub_rows,
                          const int32_t* hub_segptr, int64_t n_hub,
                          int64_t n_seg, float* hub_workspace, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Dense row-major [n_rows,K] passes between the aggregations of a layer:
+ * BatchNorm1d(train) -> ReLU -> dropout (arxiv_pyg/gnn.py:48-50) and their
+ * backward.  K % 4 == 0, K <= 1024, 16-byte aligned, contiguous (ld == K).
+ * All reductions go through `partial[slots][2][K]` scratch with
+ * slots = b200gnn_rows_slots(n_rows) (one CTA per slot, fixed order =>
+ * deterministic).
+ * ------------------------------------------------------------------ */
+int64_t b200gnn_rows_slots(int64_t n_rows);
+/* partial[s][0][:] = column sums, partial[s][1][:] = column sums of squares */
+int b200gnn_col_stats_f32(const float* Y, int64_t n_rows, int64_t K,
+                          float* partial, int64_t slots, void* stream);
+/* out[K] = column sums of Y (bias gradient of the last conv) */
+int b200gnn_col_sum_f32(const float* Y, int64_t n_rows, int64_t K, float* out,
+                        float* partial, int64_t slots, void* stream);
+/* partials (from the SpMM epilogue or col_stats) -> batch mean / invstd and the
+ * fused affine  scale = gamma*invstd, shift = beta - mean*scale ; running
+ * statistics updated like nn.BatchNorm1d (momentum, unbiased variance) unless
+ * running_mean/running_var are NULL. */
+int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int64_t K,
+                            int64_t n_rows, const float* gamma,
+                            const float* beta, float eps, float momentum,
+                            float* running_mean, float* running_var,
+                            float* mean_out, float* invstd_out,
+                            float* scale_out, float* shift_out, void* stream);
+/* out = dropout_p(relu(Y*scale + shift)); scale/shift NULL => identity affine;
+ * relu: 0/1.  The keep-mask is a pure function of (seed, effective offset,
+ * element index) (Philox4x32-10) with
+ *     effective offset = offset + (step_dev ? *step_dev * step_mul : 0),
+ * step_dev being a device int32 (e.g. the Adam step counter) so a captured
+ * CUDA graph draws a fresh mask on every replay;
+ * b200gnn_dropout_mask_u8 materialises the mask of a given effective offset. */
+int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows,
+                                    int64_t K, const float* scale,
+                                    const float* shift, int relu, float p,
+                                    uint64_t seed, uint64_t offset,
+                                    const int32_t* step_dev, uint64_t step_mul,
+                                    void* stream);
+int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p,
+                            uint64_t seed, uint64_t offset, void* stream);
+/* Backward of out = dropout_p(relu(BN_train(Y))): given dOut, out (for the
+ * mask: out>0 <=> kept and active), Y and the saved batch mean/invstd, writes
+ * dY, dgamma[K], dbeta[K] and (if non-NULL) dbias[K] = column sums of dY.
+ * coef: float[3*K] scratch.  dY must not alias dOut. */
+int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, const float* Y,
+                           const float* mean, const float* invstd,
+                           const float* gamma, int64_t n_rows, int64_t K,
+                           float p, float* dY, float* dgamma, float* dbeta,
+                           float* dbias, float* partial, int64_t slots,
+                           float* coef, void* stream);
+/* torch.optim.Adam (defaults: no amsgrad, no weight decay) over flat buffers;
+ * *step (device int32) is the number of steps already taken and is incremented
+ * (arxiv_pyg/gnn.py:192-193, 308-315). */
+int b200gnn_adam_step_f32(float* params, const float* grads, float* exp_avg,
+                          float* exp_avg_sq, int64_t n, float lr, float beta1,
+                          float beta2, float eps, int32_t* step, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Row-wise classification / logit-KD loss with its gradient in one pass.
+ *   kd_criterion(logits[train_idx], labels[train_idx], teacher[train_idx],
+ *                alpha, T)                  arxiv_pyg/criterion.py:8-21
+ *   F.cross_entropy(out, labels)            arxiv_pyg/gnn.py:112  (teacher_logits == NULL)
+ * logits / teacher_logits / dlogits are FULL [N,C] matrices (leading dims ld/ldt/ldd);
+ * train_idx (int64[n_train], NULL => rows 0..n_train-1) selects the rows, labels is the
+ * full int64[N] vector.  dlogits rows in train_idx receive d loss / d logits; the caller
+ * zeroes the other rows.  loss_out[3] = {loss, loss_cls, loss_kd}.
+ * partial: float[2*b200gnn_kd_partials(n_train)] scratch.  C <= 256.
+ * ------------------------------------------------------------------ */
+int64_t b200gnn_kd_partials(int64_t n_train);
+int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld,
+                                const int64_t* train_idx, int64_t n_train,
+                                const int64_t* labels,
+                                const float* teacher_logits, int64_t ldt,
+                                int64_t C, float alpha, float T,
+                                float* dlogits, int64_t ldd, float* loss_out,
+                                float* partial, void* stream);
 
 #ifdef __cplusplus
 }

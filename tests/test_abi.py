@@ -31,19 +31,20 @@ def test_abi_version_and_error_strings():
     assert L.b200gnn_abi_version() == 1
     assert L.b200gnn_error_string(0) == b"ok"
     assert b"argument" in L.b200gnn_error_string(-1)
-    assert L.b200gnn_spmm_stat_slots(129, 3) == 3 + 3
+    assert L.b200gnn_spmm_stat_slots(17, 3) == 3 + 3
+    assert L.b200gnn_csr_chunk_count(10, 100, 64, 4) == 3
 
 
 def test_argument_validation_without_gpu():
     L = lib.load()
     # bad reduce / null pointers are rejected before any launch
-    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 5, 5, 4, 7, None, None, 0, 1, None, None,
-                                  0, 0, None, None) == -1
-    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 5, 5, 4, 0, None, None, 0, 1, None, None,
-                                  0, 0, None, None) == -1
+    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 5, 5, 4, 7, None, None, None, 1, 0, 1, None,
+                                  None, 0, 0, None, None) == -1
+    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 5, 5, 4, 0, None, None, None, 1, 0, 1, None,
+                                  None, 0, 0, None, None) == -1
     # empty problem is a no-op
-    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 0, 0, 4, 0, None, None, 0, 1, None, None,
-                                  0, 0, None, None) == 0
+    assert L.b200gnn_spmm_csr_f32(None, None, None, None, 4, None, 4, 0, 0, 4, 0, None, None, None, 0, 0, 1, None,
+                                  None, 0, 0, None, None) == 0
 
 
 def test_cpu_tensors_are_rejected_loudly():

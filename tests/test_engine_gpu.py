@@ -1,0 +1,142 @@
+"""Fused GCN student step (engine) vs the CPU oracle: forward logits, KD loss, every gradient, one Adam update.
+Dropout: the kernel's Philox mask is materialised through the C ABI and injected into the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import efficient_gnns_b200  # noqa: F401
+from conftest import rel_err
+from efficient_gnns_b200 import ops
+from efficient_gnns_b200.engine import GCNStudentTrainer, gcn_norm
+from efficient_gnns_b200.sparse import SparseTensor
+from efficient_gnns_b200.synthetic import skewed_edges
+from oracle import criterion as oc, graph as og, nn as onn
+
+pytestmark = pytest.mark.gpu
+
+
+def build(n=3000, e=20_000, dims=(32, 64, 64, 8), p=0.5, seed=0, lr=0.01):
+    ei = skewed_edges(n, e, seed)
+    row, col, _ = og.to_sparse_adj_t(ei.numpy(), n)
+    r, c = og.to_symmetric(row, col, n)
+    adj = SparseTensor(row=torch.from_numpy(r).cuda(), col=torch.from_numpy(c).cuda(), sparse_sizes=(n, n), is_sorted=True)
+    tr = GCNStudentTrainer(adj, list(dims), dropout=p, lr=lr, seed=seed)
+    g = torch.Generator().manual_seed(seed + 9)
+    x = torch.randn(n, dims[0], generator=g)
+    y = torch.randint(0, dims[-1], (n,), generator=g)
+    t = torch.randn(n, dims[-1], generator=g) * 2
+    idx = torch.randperm(n, generator=g)[: n // 2].sort().values
+    return tr, (r, c), x, y, t, idx
+
+
+def oracle_step(tr, rc, x, y, t, idx, masks, kd=True, lr=0.01):
+    n = x.shape[0]
+    r, c, v = og.gcn_norm(rc[0], rc[1], n)
+    ptr, c, v = torch.from_numpy(og.ind2ptr(r, n)), torch.from_numpy(c), torch.from_numpy(v)
+    sd = {k: w.cpu() for k, w in tr.state_dict().items()}
+    L = tr.L
+    W = [sd[f"convs.{i}.weight"].clone().requires_grad_(True) for i in range(L)]
+    B = [sd[f"convs.{i}.bias"].clone().requires_grad_(True) for i in range(L)]
+    ga = [sd[f"bns.{i}.weight"].clone().requires_grad_(True) for i in range(L - 1)]
+    be = [sd[f"bns.{i}.bias"].clone().requires_grad_(True) for i in range(L - 1)]
+    logits, hidden = onn.gcn_forward(x, ptr, c, v, W, B, ga, be, masks, p=tr.p)
+    if kd:
+        loss, lc, la = oc.kd_criterion(logits[idx], y[idx], t[idx], tr.alpha, tr.kd_T)
+    else:
+        loss = lc = oc.cross_entropy(logits[idx], y[idx]); la = loss * 0
+    params = []
+    for i in range(L):
+        params += [W[i], B[i]]
+        if i < L - 1:
+            params += [ga[i], be[i]]
+    opt = torch.optim.Adam(params, lr=lr)
+    opt.zero_grad(); loss.backward()
+    grads = [p_.grad.clone() for p_ in params]
+    opt.step()
+    return logits.detach(), hidden.detach(), (loss.detach(), lc.detach(), la.detach()), grads, [p_.detach() for p_ in params]
+
+
+def flat(ts):
+    return torch.cat([t.reshape(-1) for t in ts])
+
+
+@pytest.mark.parametrize("p,kd", [(0.0, True), (0.5, True), (0.5, False)])
+def test_gcn_step_matches_oracle(p, kd):
+    tr, rc, x, y, t, idx = build(p=p)
+    n = x.shape[0]
+    masks = None
+    if p > 0:
+        masks = [ops.dropout_mask(n, tr.dims[l + 1], p, tr.seed, tr.dropout_offset(l, 0)).cpu().bool() for l in range(tr.L - 1)]
+        frac = float(masks[0].float().mean())
+        assert abs(frac - (1 - p)) < 0.01
+    ref_logits, ref_hidden, ref_loss, ref_grads, ref_params = oracle_step(tr, rc, x, y, t, idx, masks, kd)
+    xc, yc, tc, ic = x.cuda(), y.cuda(), t.cuda(), idx.cuda()
+    loss = tr.train_step(xc, yc, ic, tc if kd else None).cpu()
+    assert rel_err(tr.Y[-1], ref_logits) < 1e-5
+    assert rel_err(tr.A[-1], ref_hidden) < 1e-5
+    assert abs(loss[0] - ref_loss[0]) < 1e-5 * abs(ref_loss[0]) + 1e-7
+    assert abs(loss[1] - ref_loss[1]) < 1e-5 * abs(ref_loss[1]) + 1e-7
+    if kd:
+        assert abs(loss[2] - ref_loss[2]) < 1e-5 * abs(ref_loss[2]) + 1e-7
+    # gradients, tensor by tensor (a conv bias in front of BatchNorm has zero gradient up to rounding noise)
+    got = []
+    for l in range(tr.L):
+        got += [tr.gW[l], tr.gb[l]]
+        if l < tr.L - 1:
+            got += [tr.ggamma[l], tr.gbeta[l]]
+    scale = max(g.abs().max().item() for g in ref_grads)
+    for i, (a, b) in enumerate(zip(got, ref_grads)):
+        is_hidden_bias = (i % 4 == 1) and i < 4 * (tr.L - 1)
+        if is_hidden_bias:
+            assert a.abs().max().item() < 1e-5 * scale
+        else:
+            assert rel_err(a, b) < 2e-5, f"grad {i}"
+    # Adam update (skip the noise-driven hidden biases)
+    new = []
+    for l in range(tr.L):
+        new += [tr.W[l], tr.b[l]]
+        if l < tr.L - 1:
+            new += [tr.gamma[l], tr.beta[l]]
+    for i, (a, b) in enumerate(zip(new, ref_params)):
+        if (i % 4 == 1) and i < 4 * (tr.L - 1):
+            continue
+        assert (a.cpu() - b).abs().max().item() < 2e-5, f"param {i}"
+    assert int(tr.step_count.item()) == 1
+
+
+def test_graph_capture_replays_identically_and_advances_dropout():
+    tr, rc, x, y, t, idx = build(p=0.5, seed=1)
+    tr2, *_ = build(p=0.5, seed=1)
+    xc, yc, tc, ic = x.cuda(), y.cuda(), t.cuda(), idx.cuda()
+    # eager reference run: 3 steps
+    eager = [tr2.train_step(xc, yc, ic, tc).clone() for _ in range(3)]
+    # captured run: capture() itself performs warm-up steps, so reset state afterwards
+    tr.capture(xc, yc, ic, tc, warmup=1)
+    tr.reset_parameters(1)
+    for l in range(tr.L - 1):
+        tr.running_mean[l].zero_(); tr.running_var[l].fill_(1.0)
+    got = [tr.replay().clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    for a, b in zip(got, eager):
+        assert torch.equal(a, b)          # bitwise: same kernels, same order, deterministic reductions
+    assert not torch.equal(got[0], got[1])
+    assert torch.equal(tr.params, tr2.params)
+    assert int(tr.step_count.item()) == 3
+
+
+def test_eval_forward_uses_running_statistics():
+    tr, rc, x, y, t, idx = build(p=0.5, seed=2)
+    xc = x.cuda()
+    tr.train_step(xc, y.cuda(), idx.cuda(), t.cuda())
+    logits = tr.forward(xc, training=False).cpu()
+    n = x.shape[0]
+    r, c, v = og.gcn_norm(rc[0], rc[1], n)
+    ptr, c, v = torch.from_numpy(og.ind2ptr(r, n)), torch.from_numpy(c), torch.from_numpy(v)
+    sd = {k: w.cpu() for k, w in tr.state_dict().items()}
+    h = x
+    for l in range(tr.L):
+        h = onn.gcn_conv(h, ptr, c, v, sd[f"convs.{l}.weight"], sd[f"convs.{l}.bias"])
+        if l < tr.L - 1:
+            h = (h - sd[f"bns.{l}.running_mean"]) / torch.sqrt(sd[f"bns.{l}.running_var"] + 1e-5) * sd[f"bns.{l}.weight"] + sd[f"bns.{l}.bias"]
+            h = torch.relu(h)
+    assert rel_err(logits, h) < 1e-5

@@ -44,23 +44,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--widths", type=int, nargs="+", default=[256, 128, 40])
-    ap.add_argument("--thresholds", type=int, nargs="+", default=[512])
+    ap.add_argument("--thresholds", type=int, nargs="+", default=[256])
+    ap.add_argument("--chunks", type=int, nargs="+", default=[128])
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     S = synthetic.ARXIV
     n = S["num_nodes"]
     res = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    adjs = {gcn: build_adj(n, S["num_edges"], gcn=gcn) for gcn in (True, False)}
     for thr in a.thresholds:
-        sparse.HUB_THRESHOLD = thr
-        sparse.HUB_SEG_LEN = thr
+      for chunk in a.chunks:
         for gcn in (True, False):
-            adj = build_adj(n, S["num_edges"], gcn=gcn)
-            st = adj.storage
+            st = adjs[gcn].storage
             G = st.engine_csr() if gcn else st.engine_csr_unweighted()
-            # rebuild plan with this threshold
-            G.hub_threshold, G.seg_len = thr, thr
-            G.build_hub_plan()
+            G.build_plan(hub_threshold=thr, seg_len=thr, chunk_nnz=chunk)
             nnz = G.nnz
             for K in a.widths:
                 x = torch.randn(n, K, device="cuda")
@@ -71,7 +69,7 @@ def main():
                 med, best = time_fn(lambda: ops.spmm_csr(G, x, red, out=out), a.iters, flush)
                 alg = 2 * n * K * 4 + nnz * (4 + (4 if gcn else 0)) + (n + 1) * 4
                 gather = nnz * (K * 4 + 8) + n * K * 4
-                rec = dict(kernel="spmm", weighted=gcn, reduce=red, K=K, hub_threshold=thr, n_hub=G.n_hub, n_seg=G.n_seg,
+                rec = dict(kernel="spmm", weighted=gcn, reduce=red, K=K, hub_threshold=thr, chunk_nnz=chunk, n_chunks=G.n_chunks, n_hub=G.n_hub, n_seg=G.n_seg,
                            nnz=nnz, ms_median=med, ms_best=best, alg_GBps=alg / med / 1e6, gather_GBps=gather / med / 1e6,
                            edges_per_s=nnz / med * 1e3)
                 print(json.dumps(rec), flush=True)
