@@ -254,7 +254,10 @@ def run_single(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(ds, nnz, {"parallelism": "1 GPU", "cuda_graph": True,
-                                               "hub_threshold": tr.G.hub_threshold, "chunk_nnz": tr.G.chunk_nnz}),
+                                               "hub_threshold": tr.G.hub_threshold, "chunk_nnz": tr.G.chunk_nnz,
+                                               "aggregations_executed": tr.aggregations_per_step(),
+                                               "edges_note": "value counts the reference step's 6 aggregations (2*L*nnz); "
+                                               "the engine executes layer 0 as (A_hat X) W, which needs 5"}),
             "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel K=256 (4 of the 6 aggregations per step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg, "ms_per_launch": k256_ms,

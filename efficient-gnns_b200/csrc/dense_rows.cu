@@ -64,25 +64,38 @@ __global__ void __launch_bounds__(ROWS_THREADS) col_stats4_kernel(const float* _
 // ---------------------------------------------------------------- BatchNorm finalize (training mode)
 // partial[slots][2][K] -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale; running stats updated
 // like nn.BatchNorm1d (momentum, unbiased running variance).  fp64 accumulation of the partials.
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int slots, int K,
-                                                          int64_t n, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float eps, float momentum,
-                                                          float* running_mean, float* running_var, float* mean_out,
-                                                          float* invstd_out, float* scale_out, float* shift_out) {
-  __shared__ double sh[2][8][32];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + c;
+// Reduce partial[slots][2][K] over slots for 8 columns per CTA (32 row groups x 8 columns = 256 threads, 32-byte
+// sectors fully used, K/8 CTAs), fp64 accumulation, fixed order => deterministic.
+constexpr int FIN_COLS = 8, FIN_GROUPS = 32;
+__device__ __forceinline__ bool finalize_reduce(const float* __restrict__ partial, int slots, int K, bool second,
+                                                double& s_out, double& q_out, int& k_out) {
+  __shared__ double sh[2][FIN_GROUPS][FIN_COLS];
+  const int c = threadIdx.x % FIN_COLS, g = threadIdx.x / FIN_COLS;
+  const int k = blockIdx.x * FIN_COLS + c;
   double s = 0.0, q = 0.0;
   if (k < K)
-    for (int j = g; j < slots; j += 8) {
+    for (int j = g; j < slots; j += FIN_GROUPS) {
       s += (double)partial[(size_t)j * 2 * K + k];
-      q += (double)partial[(size_t)j * 2 * K + K + k];
+      if (second) q += (double)partial[(size_t)j * 2 * K + K + k];
     }
   sh[0][g][c] = s; sh[1][g][c] = q;
   __syncthreads();
   if (g == 0 && k < K) {
     s = 0.0; q = 0.0;
-    for (int j = 0; j < 8; ++j) { s += sh[0][j][c]; q += sh[1][j][c]; }
+    for (int j = 0; j < FIN_GROUPS; ++j) { s += sh[0][j][c]; q += sh[1][j][c]; }
+    s_out = s; q_out = q; k_out = k;
+    return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int slots, int K,
+                                                          int64_t n, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, float momentum,
+                                                          float* running_mean, float* running_var, float* mean_out,
+                                                          float* invstd_out, float* scale_out, float* shift_out) {
+  double s, q; int k;
+  if (finalize_reduce(partial, slots, K, true, s, q, k)) {
     const double mean = s / (double)n;
     double var = q / (double)n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -174,20 +187,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
                                                               int64_t n, const float* __restrict__ gamma,
                                                               const float* __restrict__ invstd, float* dgamma,
                                                               float* dbeta, float* coef /*[3][K]*/) {
-  __shared__ double sh[2][8][32];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + c;
-  double s = 0.0, q = 0.0;
-  if (k < K)
-    for (int j = g; j < slots; j += 8) {
-      s += (double)partial[(size_t)j * 2 * K + k];
-      q += (double)partial[(size_t)j * 2 * K + K + k];
-    }
-  sh[0][g][c] = s; sh[1][g][c] = q;
-  __syncthreads();
-  if (g == 0 && k < K) {
-    s = 0.0; q = 0.0;
-    for (int j = 0; j < 8; ++j) { s += sh[0][j][c]; q += sh[1][j][c]; }
+  double s, q; int k;
+  if (finalize_reduce(partial, slots, K, true, s, q, k)) {
     dbeta[k] = (float)s;
     dgamma[k] = (float)q;
     coef[k] = gamma[k] * invstd[k];
@@ -228,19 +229,8 @@ __global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_apply_kernel(
 // Sum partial[slots][2][K] (first plane only) -> out[K]   (bias gradients)
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int slots, int K,
                                                               float* __restrict__ out) {
-  __shared__ double sh[8][32];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + c;
-  double s = 0.0;
-  if (k < K)
-    for (int j = g; j < slots; j += 8) s += (double)partial[(size_t)j * 2 * K + k];
-  sh[g][c] = s;
-  __syncthreads();
-  if (g == 0 && k < K) {
-    s = 0.0;
-    for (int j = 0; j < 8; ++j) s += sh[j][c];
-    out[k] = (float)s;
-  }
+  double s, q; int k;
+  if (finalize_reduce(partial, slots, K, false, s, q, k)) out[k] = (float)s;
 }
 
 // ---------------------------------------------------------------- Adam (torch.optim.Adam defaults, no amsgrad/decay)
@@ -295,7 +285,7 @@ extern "C" int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int6
   if (!partial || slots < 1 || K <= 0 || n_rows <= 0 || !gamma || !beta || !mean_out || !invstd_out || !scale_out ||
       !shift_out || ((running_mean == nullptr) != (running_var == nullptr)))
     return B200GNN_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, (cudaStream_t)stream>>>(
       partial, (int)slots, (int)K, n_rows, gamma, beta, eps, momentum, running_mean, running_var, mean_out, invstd_out,
       scale_out, shift_out);
   return check_launch();
@@ -339,14 +329,14 @@ extern "C" int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, cons
   bn_act_bwd_reduce_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, n_rows, (int)K, inv_keep,
                                                                   partial, (int)slots);
   if ((rc = check_launch())) return rc;
-  bn_bwd_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, n_rows, gamma, invstd, dgamma,
+  bn_bwd_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(partial, (int)slots, (int)K, n_rows, gamma, invstd, dgamma,
                                                               dbeta, coef);
   if ((rc = check_launch())) return rc;
   bn_act_bwd_apply_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, coef, n_rows, (int)K,
                                                                  inv_keep, dY, dbias ? partial : nullptr, (int)slots);
   if ((rc = check_launch())) return rc;
   if (dbias) {
-    colsum_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, dbias);
+    colsum_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(partial, (int)slots, (int)K, dbias);
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
@@ -359,7 +349,7 @@ extern "C" int b200gnn_col_sum_f32(const float* Y, int64_t n_rows, int64_t K, fl
   int rc;
   col_stats4_kernel<<<(int)slots, ROWS_THREADS, 2 * K * sizeof(float), st>>>(Y, n_rows, (int)K, partial, (int)slots);
   if ((rc = check_launch())) return rc;
-  colsum_finalize_kernel<<<(int)((K + 31) / 32), 256, 0, st>>>(partial, (int)slots, (int)K, out);
+  colsum_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(partial, (int)slots, (int)K, out);
   return check_launch();
 }
 

@@ -89,14 +89,24 @@ __global__ void __launch_bounds__(LOSS_THREADS) kd_rows_kernel(
   }
 }
 
-// out[3] = {loss, loss_cls, loss_kd}
-__global__ void kd_finalize_kernel(const float* __restrict__ partial, int n_part, float inv_n, float inv_nC,
-                                   float alpha, float T, int has_teacher, float* __restrict__ out) {
+// out[3] = {loss, loss_cls, loss_kd}; one CTA, fixed-order tree => deterministic
+__global__ void __launch_bounds__(256) kd_finalize_kernel(const float* __restrict__ partial, int n_part, float inv_n,
+                                                          float inv_nC, float alpha, float T, int has_teacher,
+                                                          float* __restrict__ out) {
+  __shared__ double s_ce[256], s_kl[256];
   double ce = 0.0, kl = 0.0;
-  for (int i = 0; i < n_part; ++i) { ce += partial[2 * i]; kl += partial[2 * i + 1]; }
-  const float loss_cls = (float)(ce * inv_n), loss_kd = (float)(kl * inv_nC);
-  out[1] = loss_cls; out[2] = loss_kd;
-  out[0] = has_teacher ? loss_kd * (alpha * T * T) + loss_cls * (1.f - alpha) : loss_cls;
+  for (int i = threadIdx.x; i < n_part; i += 256) { ce += partial[2 * i]; kl += partial[2 * i + 1]; }
+  s_ce[threadIdx.x] = ce; s_kl[threadIdx.x] = kl;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) { s_ce[threadIdx.x] += s_ce[threadIdx.x + d]; s_kl[threadIdx.x] += s_kl[threadIdx.x + d]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float loss_cls = (float)(s_ce[0] * inv_n), loss_kd = (float)(s_kl[0] * inv_nC);
+    out[1] = loss_cls; out[2] = loss_kd;
+    out[0] = has_teacher ? loss_kd * (alpha * T * T) + loss_cls * (1.f - alpha) : loss_cls;
+  }
 }
 
 }  // namespace b200gnn
@@ -126,7 +136,7 @@ extern "C" int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld, cons
   kd_rows_kernel<<<grid, LOSS_THREADS, 0, st>>>(logits, ld, train_idx, n_train, labels, teacher_logits, ldt, (int)C,
                                                 kd ? 1.f / T : 1.f, w_cls, w_kd, dlogits, ldd, partial);
   if ((rc = check_launch())) return rc;
-  kd_finalize_kernel<<<1, 1, 0, st>>>(partial, grid, 1.f / (float)n_train, 1.f / ((float)n_train * (float)C), alpha, T,
+  kd_finalize_kernel<<<1, 256, 0, st>>>(partial, grid, 1.f / (float)n_train, 1.f / ((float)n_train * (float)C), alpha, T,
                                       kd ? 1 : 0, loss_out);
   return check_launch();
 }

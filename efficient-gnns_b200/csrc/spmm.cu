@@ -40,7 +40,7 @@ struct SpmmParams {
   float* hub_ws;
   int64_t ldx, ldy;  // in floats
   int32_t n_rows, K, nvec;
-  int32_t hub_threshold, seg_len, n_hub, n_chunks;
+  int32_t hub_threshold, seg_len, n_hub, n_seg, n_chunks;
   int32_t mean, stream_store, main_grid;
 };
 
@@ -140,9 +140,8 @@ __device__ __forceinline__ void smem_add1(float* s, int voff, const float4& a) {
 
 // ---------------------------------------------------------------- main kernel
 template <typename V, int CH, bool HAS_VAL, bool STATS>
-__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmParams p) {
+__device__ __forceinline__ void spmm_chunk_cta(const SpmmParams& p, const int cta, float* s_stat) {
   constexpr int W = VecTraits<V>::W;
-  __shared__ float s_stat[2 * SPMM_MAX_SLAB_FLOATS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LaneMap m = make_lane_map(p.nvec, lane);
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmPa
 
   // one warp per chunk: a run of consecutive rows holding ~chunk_nnz non-zeros (plan from csr_chunk_plan),
   // so every warp has about the same amount of gather work whatever the degree distribution.
-  const int chunk = blockIdx.x * SPMM_WARPS + warp;
+  const int chunk = cta * SPMM_WARPS + warp;
   const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
   const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
   int end = row_lo < row_hi ? __ldg(p.rowptr + row_lo) : 0;
@@ -207,7 +206,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmPa
       }
       __syncthreads();
     }
-    float* out = p.stat_partial + (size_t)blockIdx.x * 2 * p.K;
+    float* out = p.stat_partial + (size_t)cta * 2 * p.K;
     for (int i = threadIdx.x; i < 2 * p.K; i += SPMM_THREADS) out[i] = s_stat[i];
   }
 }
@@ -217,9 +216,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmPa
 // combine in warp order through shared memory; raw (un-normalised) partials go
 // to the workspace.
 template <typename V, int CH, bool HAS_VAL>
-__global__ void __launch_bounds__(SPMM_THREADS) spmm_hub_seg_kernel(const SpmmParams p) {
+__device__ __forceinline__ void spmm_hub_seg_cta(const SpmmParams& p, const int seg, float* s_buf) {
   constexpr int W = VecTraits<V>::W;
-  __shared__ float s_buf[SPMM_MAX_SLAB_FLOATS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LaneMap m = make_lane_map(p.nvec, lane);
@@ -228,7 +226,6 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_hub_seg_kernel(const SpmmPa
   const V* Xv = reinterpret_cast<const V*>(p.X);
   const size_t ldxv = (size_t)(p.ldx / W);
 
-  const int seg = blockIdx.x;
   int lo = 0, hi = p.n_hub;  // largest h with hub_segptr[h] <= seg
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -273,6 +270,15 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_hub_seg_kernel(const SpmmPa
   }
 }
 
+// One launch: the first n_seg CTAs take the hub segments (the longest work items start first), the rest take
+// chunks of ordinary rows.
+template <typename V, int CH, bool HAS_VAL, bool STATS>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmParams p) {
+  __shared__ float s_mem[2 * SPMM_MAX_SLAB_FLOATS];
+  if ((int)blockIdx.x < p.n_seg) spmm_hub_seg_cta<V, CH, HAS_VAL>(p, (int)blockIdx.x, s_mem);
+  else spmm_chunk_cta<V, CH, HAS_VAL, STATS>(p, (int)blockIdx.x - p.n_seg, s_mem);
+}
+
 // Sum a hub row's segment partials in segment order, apply the epilogue.
 __global__ void __launch_bounds__(256) spmm_hub_finalize_kernel(const SpmmParams p) {
   const int h = blockIdx.x;
@@ -309,26 +315,18 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
 }
 
 template <typename V, int CH>
-static int launch_spmm(const SpmmParams& p, int n_seg, cudaStream_t st) {
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   int rc;
   const bool stats = p.stat_partial != nullptr;
+  const int grid = p.main_grid + p.n_seg;
   if (p.val) {
-    if (stats) spmm_rows_kernel<V, CH, true, true><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
-    else spmm_rows_kernel<V, CH, true, false><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
-    if ((rc = check_launch())) return rc;
-    if (n_seg > 0) {
-      spmm_hub_seg_kernel<V, CH, true><<<n_seg, SPMM_THREADS, 0, st>>>(p);
-      if ((rc = check_launch())) return rc;
-    }
+    if (stats) spmm_rows_kernel<V, CH, true, true><<<grid, SPMM_THREADS, 0, st>>>(p);
+    else spmm_rows_kernel<V, CH, true, false><<<grid, SPMM_THREADS, 0, st>>>(p);
   } else {
-    if (stats) spmm_rows_kernel<V, CH, false, true><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
-    else spmm_rows_kernel<V, CH, false, false><<<p.main_grid, SPMM_THREADS, 0, st>>>(p);
-    if ((rc = check_launch())) return rc;
-    if (n_seg > 0) {
-      spmm_hub_seg_kernel<V, CH, false><<<n_seg, SPMM_THREADS, 0, st>>>(p);
-      if ((rc = check_launch())) return rc;
-    }
+    if (stats) spmm_rows_kernel<V, CH, false, true><<<grid, SPMM_THREADS, 0, st>>>(p);
+    else spmm_rows_kernel<V, CH, false, false><<<grid, SPMM_THREADS, 0, st>>>(p);
   }
+  if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
     spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);
     if ((rc = check_launch())) return rc;
@@ -337,10 +335,10 @@ static int launch_spmm(const SpmmParams& p, int n_seg, cudaStream_t st) {
 }
 
 template <typename V>
-static int dispatch_ch(const SpmmParams& p, int n_seg, cudaStream_t st) {
-  if (p.nvec <= 32) return launch_spmm<V, 1>(p, n_seg, st);
-  if (p.nvec <= 64) return launch_spmm<V, 2>(p, n_seg, st);
-  return launch_spmm<V, 4>(p, n_seg, st);
+static int dispatch_ch(const SpmmParams& p, cudaStream_t st) {
+  if (p.nvec <= 32) return launch_spmm<V, 1>(p, st);
+  if (p.nvec <= 64) return launch_spmm<V, 2>(p, st);
+  return launch_spmm<V, 4>(p, st);
 }
 
 // ------------------------------------------------------------ hub plan kernels
@@ -488,6 +486,7 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   p.ldx = ldx; p.ldy = ldy;
   p.n_rows = (int32_t)n_rows; p.K = (int32_t)K;
   p.hub_threshold = hub_threshold; p.seg_len = seg_len; p.n_hub = (int32_t)n_hub;
+  p.n_seg = n_hub > 0 ? (int32_t)n_seg : 0;
   p.mean = reduce == B200GNN_REDUCE_MEAN;
   p.stream_store = (n_rows * K * 4 > (int64_t)64 << 20) ? 1 : 0;
   p.main_grid = (int32_t)((n_chunks + SPMM_WARPS - 1) / SPMM_WARPS);
@@ -503,9 +502,9 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   if (!single_slab) p.stat_partial = nullptr;  // stats by a separate pass below
 
   int rc;
-  if (W == 4) rc = dispatch_ch<float4>(p, (int)n_seg, st);
-  else if (W == 2) rc = dispatch_ch<float2>(p, (int)n_seg, st);
-  else rc = dispatch_ch<float>(p, (int)n_seg, st);
+  if (W == 4) rc = dispatch_ch<float4>(p, st);
+  else if (W == 2) rc = dispatch_ch<float2>(p, st);
+  else rc = dispatch_ch<float>(p, st);
   if (rc) return rc;
 
   if (fused_stats && !single_slab) {

@@ -51,7 +51,8 @@ class GCNStudentTrainer:
     """State + fused step of an L-layer GCN student on one GPU."""
 
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
-                 alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+                 alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
+                 aggregate_first: Optional[bool] = None):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         self.device = adj.device
         self.dims, self.L = list(dims), len(dims) - 1
@@ -61,6 +62,13 @@ class GCNStudentTrainer:
         for d in dims[1:]:
             assert d % 4 == 0 and d <= 1024, "layer widths must be multiples of 4 (128-bit rows)"
         self.N = adj.size(0)
+        # Layer 0 may aggregate BEFORE its GEMM: Â(XW) = (ÂX)W.  When the input is narrower than the hidden width
+        # the gather runs at the narrow width, and because X needs no gradient the backward aggregation of layer 0
+        # disappears altogether: dW0 = (ÂX)ᵀ dY0.  Same mathematics as the reference (PyG transforms first and
+        # pays a 256-wide backward SpMM whose result is only used as an intermediate); fp32 reassociation only.
+        self.agg_first = (dims[0] < dims[1] and dims[0] % 4 == 0) if aggregate_first is None else bool(aggregate_first)
+        if self.L < 2:
+            self.agg_first = False
 
         norm = gcn_norm(adj)                     # cached=True semantics: normalise once (arxiv_pyg/gnn.py:28)
         self.G: CsrGraph = norm.storage.engine_csr()
@@ -110,6 +118,7 @@ class GCNStudentTrainer:
         self.dY = [buf(dims[l + 1]) for l in range(self.L)]
         self.dH = [buf(dims[l + 1]) for l in range(self.L)]
         self.dA = [buf(dims[l + 1]) for l in range(self.L - 1)]
+        self.AX = buf(dims[0]) if self.agg_first else None              # Â X (layer 0, aggregate-first)
         slots_spmm = ops.stat_slots(self.G)
         self.stat_part = [torch.empty(slots_spmm, 2, dims[l + 1], device=dev) for l in range(self.L - 1)]
         self.bn = [torch.empty(4, dims[l + 1], device=dev) for l in range(self.L - 1)]   # mean, invstd, scale, shift
@@ -164,8 +173,23 @@ class GCNStudentTrainer:
         """Returns logits [N,C]; hidden activations stay in self.A (self.A[-1] is the reference's model.out_feat)."""
         inp = x
         for l in range(self.L):
-            torch.mm(inp, self.W[l], out=self.H[l])
             last = l == self.L - 1
+            if l == 0 and self.agg_first:
+                ops.spmm_csr(self.G, x, "sum", out=self.AX)
+                torch.addmm(self.b[0], self.AX, self.W[0], out=self.Y[0])
+                if training:
+                    ops.col_stats(self.Y[0], partial=self._part(self.dims[1]))
+                    ops.bn_finalize(self._part(self.dims[1]), self.N, self.gamma[0], self.beta[0], self.bn_eps,
+                                    self.bn_momentum, self.running_mean[0], self.running_var[0], out=self.bn[0])
+                    ops.affine_relu_dropout(self.Y[0], self.bn[0][2], self.bn[0][3], True, self.p, self.seed, 0,
+                                            out=self.A[0], step_dev=self.step_count, step_mul=self.L)
+                else:
+                    scale = self.gamma[0] * torch.rsqrt(self.running_var[0] + self.bn_eps)
+                    shift = self.beta[0] - self.running_mean[0] * scale
+                    ops.affine_relu_dropout(self.Y[0], scale, shift, True, 0.0, out=self.A[0])
+                inp = self.A[0]
+                continue
+            torch.mm(inp, self.W[l], out=self.H[l])
             if last:
                 ops.spmm_csr(self.G, self.H[l], "sum", bias=self.b[l], out=self.Y[l])
             elif training:
@@ -189,6 +213,9 @@ class GCNStudentTrainer:
             inp = x if l == 0 else self.A[l - 1]
             if l == self.L - 1:
                 ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(self.dims[l + 1]))
+            if l == 0 and self.agg_first:
+                torch.mm(self.AX.t(), self.dY[0], out=self.gW[0])      # dW0 = (ÂX)ᵀ dY0, no backward aggregation
+                continue
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
             torch.mm(inp.t(), self.dH[l], out=self.gW[l])
             if l > 0:
@@ -253,7 +280,17 @@ class GCNStudentTrainer:
         self._step_impl(st["x"], st["y"], st["train_idx"], st["teacher"])
         return lib.launch_count() - before
 
+    def aggregations_per_step(self) -> Dict[int, int]:
+        """width -> number of SpMM launches of that width in one training step."""
+        out: Dict[int, int] = {}
+        for l in range(self.L):
+            if l == 0 and self.agg_first:
+                out[self.dims[0]] = out.get(self.dims[0], 0) + 1
+            else:
+                out[self.dims[l + 1]] = out.get(self.dims[l + 1], 0) + 2
+        return out
+
     def spmm_algorithmic_bytes(self) -> Dict[int, int]:
         """Compulsory HBM bytes of one aggregation per feature width:
         2*N*K*4 (read X, write Y) + nnz*(4 col + 4 val) + (N+1)*4."""
-        return {k: 2 * self.N * k * 4 + self.nnz * 8 + (self.N + 1) * 4 for k in set(self.dims[1:])}
+        return {k: 2 * self.N * k * 4 + self.nnz * 8 + (self.N + 1) * 4 for k in set(self.dims)}

@@ -15,12 +15,12 @@ from oracle import criterion as oc, graph as og, nn as onn
 pytestmark = pytest.mark.gpu
 
 
-def build(n=3000, e=20_000, dims=(32, 64, 64, 8), p=0.5, seed=0, lr=0.01):
+def build(n=3000, e=20_000, dims=(32, 64, 64, 8), p=0.5, seed=0, lr=0.01, agg_first=None):
     ei = skewed_edges(n, e, seed)
     row, col, _ = og.to_sparse_adj_t(ei.numpy(), n)
     r, c = og.to_symmetric(row, col, n)
     adj = SparseTensor(row=torch.from_numpy(r).cuda(), col=torch.from_numpy(c).cuda(), sparse_sizes=(n, n), is_sorted=True)
-    tr = GCNStudentTrainer(adj, list(dims), dropout=p, lr=lr, seed=seed)
+    tr = GCNStudentTrainer(adj, list(dims), dropout=p, lr=lr, seed=seed, aggregate_first=agg_first)
     g = torch.Generator().manual_seed(seed + 9)
     x = torch.randn(n, dims[0], generator=g)
     y = torch.randint(0, dims[-1], (n,), generator=g)
@@ -60,9 +60,11 @@ def flat(ts):
     return torch.cat([t.reshape(-1) for t in ts])
 
 
+@pytest.mark.parametrize("agg_first", [False, True])
 @pytest.mark.parametrize("p,kd", [(0.0, True), (0.5, True), (0.5, False)])
-def test_gcn_step_matches_oracle(p, kd):
-    tr, rc, x, y, t, idx = build(p=p)
+def test_gcn_step_matches_oracle(p, kd, agg_first):
+    tr, rc, x, y, t, idx = build(p=p, agg_first=agg_first)
+    assert tr.agg_first == agg_first
     n = x.shape[0]
     masks = None
     if p > 0:
