@@ -1,0 +1,372 @@
+// fp32-faithful dense GEMM on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+//
+//   C[M,N] = A[M,K] · B[N,K]^T (+ bias[N])          all fp32 in HBM, fp32 accumulation in TMEM
+//
+// The reference computes its dense contractions (GCNConv's X·W, nn.Linear, the backward dX = dY·W^T;
+// arxiv_pyg/gnn.py:47,52 via PyG) in fp32 and the parity bar is 1e-5, which a single TF32 pass (10-bit
+// mantissa) cannot meet.  So every product is evaluated with the 3xTF32 split
+//        a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo ,   x_hi = x with the low 13 mantissa bits cleared,
+//                                                    x_lo = (x - x_hi) with the low 13 bits cleared,
+// three tcgen05.mma.kind::tf32 instructions per K-step into the same TMEM accumulator.  The dropped terms
+// are O(2^-22) relative.  B (the small weight matrix) arrives pre-split from b200gnn_split_tf32_f32; A (the
+// big activation matrix) is split on the fly in shared memory, so HBM only ever sees one fp32 copy of it.
+//
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128x32 fp32 boxes (128B swizzle) of A, B_hi, B_lo
+//   warp 1      MMA issuer  : one elected thread, 12 tcgen05.mma per stage, tcgen05.commit -> mbarriers
+//   warp 2      TMEM allocator (256 columns = two 128x128 fp32 accumulators, double buffered)
+//   warps 4-7   splitter    : A tile -> (A_hi in place, A_lo) in smem, fence.proxy.async, arrive
+//   warps 8-11  epilogue    : tcgen05.ld 32x32b.x32 -> registers -> (+bias) -> 128-bit global stores
+// Three pipelines: smem stages (TMA -> split -> MMA -> free), TMEM accumulators (MMA <-> epilogue), tiles.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200gnn {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 32, UMMA_K = 8;
+constexpr int STAGES = 3, ACC_STAGES = 2;
+constexpr int THREADS = 384;
+constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (A and B tiles are both 128 x 32 fp32)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024 B alignment
+constexpr int TMEM_COLS = ACC_STAGES * BN;              // 256
+constexpr uint32_t TF32_MASK = 0xFFFFE000u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  (bits 0-13)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B (bits 32-45)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// tcgen05 instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN.
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  float* C;
+  const float* bias;
+  int64_t ldc;
+  int32_t M, N, K;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                      // TMA landed            [STAGES]
+  uint64_t* split = bars + STAGES;            // A_hi/A_lo written     [STAGES]
+  uint64_t* empty = bars + 2 * STAGES;        // MMAs done with stage  [STAGES]
+  uint64_t* acc_full = bars + 3 * STAGES;     // accumulator ready     [ACC_STAGES]
+  uint64_t* acc_empty = acc_full + ACC_STAGES;  // accumulator drained [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], 3 * TILE_BYTES);
+          tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
+          tma_load_2d(&tmBhi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
+          tma_load_2d(&tmBlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          mbar_wait(&split[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 4;  // 32 B per K-step inside the 128 B swizzle atom
+            const uint64_t a_hi = make_smem_desc(st + koff), a_lo = make_smem_desc(st + TILE_BYTES + koff);
+            const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc(st + 3 * TILE_BYTES + koff);
+            mma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | k) != 0);
+            mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
+            mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+          mma_commit(&empty[s]);                       // frees the smem stage once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        mma_commit(&acc_full[a]);                      // accumulator complete -> epilogue
+        if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ splitter: A -> (A_hi, A_lo)
+    const int t = threadIdx.x - 128;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          const int o = i * 128 + t;
+          uint4 v = hi[o];
+          uint4 h, l;
+          h.x = v.x & TF32_MASK; h.y = v.y & TF32_MASK; h.z = v.z & TF32_MASK; h.w = v.w & TF32_MASK;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & TF32_MASK;
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & TF32_MASK;
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & TF32_MASK;
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & TF32_MASK;
+          hi[o] = h;
+          lo[o] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+        mbar_arrive(&split[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    int a = 0; uint32_t aph = 0;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), r);
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+          if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                v.x += __ldg(p.bias + col0 + j); v.y += __ldg(p.bias + col0 + j + 1);
+                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
+              }
+              *reinterpret_cast<float4*>(dst + j) = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
+      if (++a == ACC_STAGES) { a = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// hi/lo split of a small matrix (weights), optionally transposed: out[c][r] when transpose.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ W, int64_t rows, int64_t cols,
+                                                         int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const uint32_t v = __float_as_uint(W[i]);
+    const uint32_t h = v & TF32_MASK;
+    const uint32_t l = __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) & TF32_MASK;
+    const int64_t o = transpose ? c * rows + r : i;
+    hi[o] = __uint_as_float(h);
+    lo[o] = __uint_as_float(l);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, cols] fp32 row-major with leading dimension ld -> boxes of 32 columns x 128 rows, 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gemm
+}  // namespace b200gnn
+
+using namespace b200gnn;
+
+extern "C" int b200gnn_split_tf32_f32(const float* W, int64_t rows, int64_t cols, int transpose, float* hi, float* lo,
+                                      void* stream) {
+  if (!W || !hi || !lo || rows <= 0 || cols <= 0) return B200GNN_ERR_BAD_ARG;
+  const int64_t n = rows * cols;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  gemm::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, rows, cols, transpose, hi, lo);
+  return check_launch();
+}
+
+extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                                       void* stream) {
+  if (!A || !B_hi || !B_lo || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N ||
+      M >= INT32_MAX || N >= INT32_MAX || K >= INT32_MAX)
+    return B200GNN_ERR_BAD_ARG;
+  // TMA: 16-byte aligned bases and row pitches
+  if (lda % 4 || ldb % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16))
+    return B200GNN_ERR_UNSUPPORTED;
+  CUtensorMap tA, tBh, tBl;
+  if (!gemm::make_map(&tA, A, M, K, lda) || !gemm::make_map(&tBh, B_hi, N, K, ldb) ||
+      !gemm::make_map(&tBl, B_lo, N, K, ldb))
+    return B200GNN_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         gemm::SMEM_BYTES);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
+    attr_set = true;
+  }
+  gemm::Params p;
+  p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
+  const int tiles = (int)(((M + gemm::BM - 1) / gemm::BM) * ((N + gemm::BN - 1) / gemm::BN));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = tiles < sms ? tiles : sms;
+  gemm::gemm_tf32x3_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, (cudaStream_t)stream>>>(tA, tBh, tBl, p);
+  return check_launch();
+}

@@ -52,13 +52,14 @@ class GCNStudentTrainer:
 
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
                  alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
-                 aggregate_first: Optional[bool] = None):
+                 aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         self.device = adj.device
         self.dims, self.L = list(dims), len(dims) - 1
         self.p, self.lr, self.alpha, self.kd_T = float(dropout), float(lr), float(alpha), float(kd_T)
         self.bn_eps, self.bn_momentum = bn_eps, bn_momentum
         self.seed = int(seed)
+        self.tc_gemm = bool(tensor_core_gemm) and all(d % 4 == 0 for d in dims)
         for d in dims[1:]:
             assert d % 4 == 0 and d <= 1024, "layer widths must be multiples of 4 (128-bit rows)"
         self.N = adj.size(0)
@@ -105,6 +106,12 @@ class GCNStudentTrainer:
                 g, gg = take(dims[l + 1], (dims[l + 1],))
                 be, gbe = take(dims[l + 1], (dims[l + 1],))
                 self.gamma.append(g); self.ggamma.append(gg); self.beta.append(be); self.gbeta.append(gbe)
+        # tf32 hi/lo splits of the weights for the tcgen05 GEMM: W^T [out,in] feeds the forward (C = X W),
+        # W [in,out] feeds the input gradient (dX = dH W^T); refreshed every step (a few KB).
+        self.Wt_split = [(torch.empty(dims[l + 1], dims[l], device=dev), torch.empty(dims[l + 1], dims[l], device=dev))
+                         for l in range(self.L)]
+        self.W_split = [(torch.empty(dims[l], dims[l + 1], device=dev), torch.empty(dims[l], dims[l + 1], device=dev))
+                        for l in range(self.L)]
         self.running_mean = [torch.zeros(d, device=dev) for d in dims[1:-1]]
         self.running_var = [torch.ones(d, device=dev) for d in dims[1:-1]]
         self.reset_parameters(seed)
@@ -176,7 +183,7 @@ class GCNStudentTrainer:
             last = l == self.L - 1
             if l == 0 and self.agg_first:
                 ops.spmm_csr(self.G, x, "sum", out=self.AX)
-                torch.addmm(self.b[0], self.AX, self.W[0], out=self.Y[0])
+                self._linear(0, self.AX, self.Y[0], bias=self.b[0])
                 if training:
                     ops.col_stats(self.Y[0], partial=self._part(self.dims[1]))
                     ops.bn_finalize(self._part(self.dims[1]), self.N, self.gamma[0], self.beta[0], self.bn_eps,
@@ -189,7 +196,7 @@ class GCNStudentTrainer:
                     ops.affine_relu_dropout(self.Y[0], scale, shift, True, 0.0, out=self.A[0])
                 inp = self.A[0]
                 continue
-            torch.mm(inp, self.W[l], out=self.H[l])
+            self._linear(l, inp, self.H[l])
             if last:
                 ops.spmm_csr(self.G, self.H[l], "sum", bias=self.b[l], out=self.Y[l])
             elif training:
@@ -219,12 +226,30 @@ class GCNStudentTrainer:
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
             torch.mm(inp.t(), self.dH[l], out=self.gW[l])
             if l > 0:
-                torch.mm(self.dH[l], self.W[l].t(), out=self.dA[l - 1])
+                self._linear_dgrad(l, self.dH[l], self.dA[l - 1])
                 k = self.dims[l]
                 part = self._part(k)
                 ops.bn_act_bwd(self.dA[l - 1], self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
                                self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
                                d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
+
+    def _linear(self, l: int, inp: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        """out = inp @ W_l (+bias): tcgen05 3xTF32 kernel, or cuBLAS fp32 when disabled."""
+        if self.tc_gemm:
+            hi, lo = ops.split_tf32(self.W[l], transpose=True, hi=self.Wt_split[l][0], lo=self.Wt_split[l][1])
+            ops.gemm_tf32x3(inp, hi, lo, bias=bias, out=out)
+        elif bias is not None:
+            torch.addmm(bias, inp, self.W[l], out=out)
+        else:
+            torch.mm(inp, self.W[l], out=out)
+
+    def _linear_dgrad(self, l: int, d_out: torch.Tensor, d_inp: torch.Tensor):
+        """d_inp = d_out @ W_l^T."""
+        if self.tc_gemm:
+            hi, lo = ops.split_tf32(self.W[l], transpose=False, hi=self.W_split[l][0], lo=self.W_split[l][1])
+            ops.gemm_tf32x3(d_out, hi, lo, out=d_inp)
+        else:
+            torch.mm(d_out, self.W[l].t(), out=d_inp)
 
     def _part(self, k: int) -> torch.Tensor:
         key = f"part{k}"

@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200gnn_kd_partials": (_i64, [_i64]),
     "b200gnn_kd_loss_fwd_bwd_f32": (_int, [_f32p, _i64, _ptr, _i64, _ptr, _f32p, _i64, _i64, _f32, _f32, _f32p, _i64,
                                            _f32p, _f32p, _ptr]),
+    "b200gnn_split_tf32_f32": (_int, [_f32p, _i64, _i64, _int, _f32p, _f32p, _ptr]),
+    "b200gnn_gemm_tf32x3_f32": (_int, [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _f32p, _ptr]),
 }
 
 _lib = None

@@ -188,3 +188,30 @@ def kd_loss_fwd_bwd(logits, labels, train_idx, teacher_logits=None, alpha: float
         teacher_logits.stride(0) if teacher_logits is not None else 0, C, alpha, T, _f32(d_logits, "d_logits"),
         d_logits.stride(0), _f32(loss_out, "loss_out"), _f32(partial, "partial"), lib.stream_ptr()), "kd_loss_fwd_bwd_f32")
     return loss_out, d_logits
+
+
+# ----------------------------------------------------------------------------- tcgen05 3xTF32 GEMM
+def split_tf32(w: torch.Tensor, transpose: bool = False, hi: Optional[torch.Tensor] = None,
+               lo: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(hi, lo) tf32 split of a small [rows, cols] matrix; transposed ([cols, rows]) output if requested."""
+    rows, cols = w.shape
+    shape = (cols, rows) if transpose else (rows, cols)
+    hi = torch.empty(shape, dtype=torch.float32, device=w.device) if hi is None else hi
+    lo = torch.empty(shape, dtype=torch.float32, device=w.device) if lo is None else lo
+    lib.check(lib.load().b200gnn_split_tf32_f32(_f32(w, "w"), rows, cols, int(transpose), _f32(hi, "hi"), _f32(lo, "lo"),
+                                                lib.stream_ptr()), "split_tf32_f32")
+    return hi, lo
+
+
+def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[N,K]^T (+bias) with fp32 fidelity on the tensor cores (b pre-split by split_tf32)."""
+    M, K = a.shape
+    N = b_hi.shape[0]
+    assert b_hi.shape == b_lo.shape and b_hi.shape[1] == K
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    lib.check(lib.load().b200gnn_gemm_tf32x3_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                 b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K,
+                                                 _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_f32")
+    return out

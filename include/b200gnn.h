@@ -188,6 +188,24 @@ int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld,
                                 float* dlogits, int64_t ldd, float* loss_out,
                                 float* partial, void* stream);
 
+/* ------------------------------------------------------------------ *
+ * fp32-faithful dense GEMM on tcgen05 tensor cores (3xTF32 split, fp32
+ * accumulation in TMEM):   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])
+ * Replaces the fp32 cuBLAS contractions behind GCNConv's `x @ weight`,
+ * nn.Linear and their input gradients (arxiv_pyg/gnn.py:47,52,79,84 via PyG).
+ *   A    : fp32, row-major, split into tf32 hi/lo on the fly inside the kernel.
+ *   B_hi, B_lo : the [N,K] operand pre-split by b200gnn_split_tf32_f32
+ *          (weights are tiny; `transpose` lets [K,N] storage feed it).
+ * lda/ldb multiples of 4 floats, 16-byte aligned bases (TMA); any M, N, K.
+ * Dropped terms are O(2^-22) relative, i.e. within the 1e-5 parity budget.
+ * ------------------------------------------------------------------ */
+int b200gnn_split_tf32_f32(const float* W, int64_t rows, int64_t cols,
+                           int transpose, float* hi, float* lo, void* stream);
+int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
+                            const float* B_lo, int64_t ldb, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K,
+                            const float* bias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
