@@ -112,6 +112,9 @@ class GCNStudentTrainer:
                          for l in range(self.L)]
         self.W_split = [(torch.empty(dims[l], dims[l + 1], device=dev), torch.empty(dims[l], dims[l + 1], device=dev))
                         for l in range(self.L)]
+        wg = [ops.wgrad_supported(dims[l], dims[l + 1]) for l in range(self.L)]
+        self.wgrad_ws = (torch.empty(148 * max(dims[l] * dims[l + 1] for l in range(self.L) if wg[l]), device=dev)
+                         if self.tc_gemm and any(wg) else None)
         self.running_mean = [torch.zeros(d, device=dev) for d in dims[1:-1]]
         self.running_var = [torch.ones(d, device=dev) for d in dims[1:-1]]
         self.reset_parameters(seed)
@@ -221,10 +224,10 @@ class GCNStudentTrainer:
             if l == self.L - 1:
                 ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(self.dims[l + 1]))
             if l == 0 and self.agg_first:
-                torch.mm(self.AX.t(), self.dY[0], out=self.gW[0])      # dW0 = (ÂX)ᵀ dY0, no backward aggregation
+                self._linear_wgrad(0, self.AX, self.dY[0])             # dW0 = (ÂX)ᵀ dY0, no backward aggregation
                 continue
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
-            torch.mm(inp.t(), self.dH[l], out=self.gW[l])
+            self._linear_wgrad(l, inp, self.dH[l])
             if l > 0:
                 self._linear_dgrad(l, self.dH[l], self.dA[l - 1])
                 k = self.dims[l]
@@ -250,6 +253,14 @@ class GCNStudentTrainer:
             ops.gemm_tf32x3(d_out, hi, lo, out=d_inp)
         else:
             torch.mm(d_out, self.W[l].t(), out=d_inp)
+
+    def _linear_wgrad(self, l: int, inp: torch.Tensor, d_out: torch.Tensor):
+        """grad W_l = inp^T @ d_out: split-K tcgen05 kernel where the tiling allows, cuBLAS fp32 otherwise
+        (the 256x40 classifier weight: 3.5 GFLOP of the step's ~100)."""
+        if self.tc_gemm and ops.wgrad_supported(self.dims[l], self.dims[l + 1]):
+            ops.gemm_wgrad_tf32x3(inp, d_out, out=self.gW[l], workspace=self.wgrad_ws)
+        else:
+            torch.mm(inp.t(), d_out, out=self.gW[l])
 
     def _part(self, k: int) -> torch.Tensor:
         key = f"part{k}"

@@ -56,6 +56,8 @@ SIGNATURES = {
                                            _f32p, _f32p, _ptr]),
     "b200gnn_split_tf32_f32": (_int, [_f32p, _i64, _i64, _int, _f32p, _f32p, _ptr]),
     "b200gnn_gemm_tf32x3_f32": (_int, [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _f32p, _ptr]),
+    "b200gnn_wgrad_workspace_floats": (_i64, [_i64, _i64]),
+    "b200gnn_gemm_wgrad_tf32x3_f32": (_int, [_f32p, _i64, _f32p, _i64, _f32p, _i64, _i64, _i64, _f32p, _ptr]),
 }
 
 _lib = None

@@ -215,3 +215,24 @@ def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: O
                                                  b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K,
                                                  _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_f32")
     return out
+
+
+def wgrad_supported(k_in: int, n_out: int) -> bool:
+    return k_in in (128, 256) and n_out % 32 == 0 and 0 < n_out <= 256
+
+
+def gemm_wgrad_tf32x3(x: torch.Tensor, g: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[Kin,Nout] = x[Nn,Kin]^T @ g[Nn,Nout] on the tensor cores with fp32 fidelity (split-K over nodes)."""
+    nn_, k_in = x.shape
+    n_out = g.shape[1]
+    assert g.shape[0] == nn_
+    L = lib.load()
+    if out is None:
+        out = torch.empty(k_in, n_out, dtype=torch.float32, device=x.device)
+    if workspace is None:
+        workspace = torch.empty(int(L.b200gnn_wgrad_workspace_floats(k_in, n_out)), dtype=torch.float32, device=x.device)
+    lib.check(L.b200gnn_gemm_wgrad_tf32x3_f32(_f32(x, "x"), x.stride(0), _f32(g, "g"), g.stride(0), _f32(out, "out"), nn_,
+                                              k_in, n_out, _f32(workspace, "workspace"), lib.stream_ptr()),
+              "gemm_wgrad_tf32x3_f32")
+    return out

@@ -206,6 +206,16 @@ int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
                             int64_t ldc, int64_t M, int64_t N, int64_t K,
                             const float* bias, void* stream);
 
+/* Weight gradient  dW[Kin,Nout] = X[Nn,Kin]^T * G[Nn,Nout]  (GCNConv weight.grad / nn.Linear weight.grad^T),
+ * split-K over the node index on tcgen05 (3xTF32), partials reduced in fixed order.
+ * Kin in {128,256}, Nout a multiple of 32 up to 256 (else B200GNN_ERR_UNSUPPORTED: caller keeps the library GEMM).
+ * workspace: float[b200gnn_wgrad_workspace_floats(Kin,Nout)]. */
+int64_t b200gnn_wgrad_workspace_floats(int64_t Kin, int64_t Nout);
+int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const float* G,
+                                  int64_t ldg, float* dW, int64_t Nn,
+                                  int64_t Kin, int64_t Nout, float* workspace,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,3 +45,24 @@ def test_gemm_deterministic_and_reusable():
     o1 = ops.gemm_tf32x3(a, hi, lo)
     o2 = ops.gemm_tf32x3(a, hi, lo)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("Nn,Kin,Nout", [(16, 128, 32), (1000, 128, 256), (5003, 256, 256), (40_000, 256, 64), (7, 128, 128)])
+def test_wgrad_matches_fp64(Nn, Kin, Nout):
+    g = torch.Generator().manual_seed(Nn + Kin + Nout)
+    x = torch.randn(Nn, Kin, generator=g)
+    d = torch.randn(Nn, Nout, generator=g)
+    ref = x.double().t() @ d.double()
+    out = ops.gemm_wgrad_tf32x3(x.cuda(), d.cuda())
+    torch.cuda.synchronize()
+    e, e32 = rel_err(out, ref), rel_err(x.t() @ d, ref)
+    assert e < 1e-5, (e, e32)
+    out2 = ops.gemm_wgrad_tf32x3(x.cuda(), d.cuda())
+    assert torch.equal(out, out2)
+
+
+def test_wgrad_unsupported_shapes_are_reported():
+    from efficient_gnns_b200 import lib
+    assert not ops.wgrad_supported(256, 40) and ops.wgrad_supported(128, 256)
+    with pytest.raises(lib.B200GnnError):
+        ops.gemm_wgrad_tf32x3(torch.randn(100, 256, device="cuda"), torch.randn(100, 40, device="cuda"))

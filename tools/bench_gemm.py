@@ -41,5 +41,18 @@ def main():
                               hbm_GBps=(M * K + M * N) * 4 / t_tc / 1e6, rel_err=err)), flush=True)
 
 
+def wgrad():
+    M = 169_343
+    for (K, N) in [(128, 256), (256, 256)]:
+        x = torch.randn(M, K, device="cuda"); d = torch.randn(M, N, device="cuda")
+        out = torch.empty(K, N, device="cuda")
+        ws = torch.empty(148 * K * N, device="cuda")
+        t_tc = timeit(lambda: ops.gemm_wgrad_tf32x3(x, d, out=out, workspace=ws))
+        t_cb = timeit(lambda: torch.mm(x.t(), d, out=out))
+        print(json.dumps(dict(kind="wgrad", Nn=M, Kin=K, Nout=N, ms_tcgen05=t_tc, ms_cublas_fp32=t_cb,
+                              hbm_GBps=(M * K + M * N) * 4 / t_tc / 1e6)), flush=True)
+
+
 if __name__ == "__main__":
+    wgrad()
     main()
