@@ -40,8 +40,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
 }
 
 struct Params {
-  float* partial;   // [grid][Kin][Nout]
-  int32_t Nn, Kin, Nout, num_kb;
+  float* partial;   // [grid][Kin][Npad],  Npad = Nout rounded up to 32 (TMA zero-fills the missing columns)
+  int32_t Nn, Kin, Nout, Npad, num_kb;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -75,7 +75,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int kb0 = (int)((int64_t)p.num_kb * blockIdx.x / gridDim.x);
   const int kb1 = (int)((int64_t)p.num_kb * (blockIdx.x + 1) / gridDim.x);
   const int mtiles = p.Kin / 128;
-  const int xg = p.Kin / 32, gg = p.Nout / 32;               // 32-column groups of X and G
+  const int xg = p.Kin / 32, gg = p.Npad / 32;               // 32-column groups of X and G
   const uint32_t tx_bytes = (uint32_t)(xg + gg) * BKN * 128;
 
   if (warp == 0) {
@@ -94,7 +94,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (lane == 0) {
       // D = f32, A = B = tf32, both MN-major, M = 128, N = Nout
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(p.Nout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int s = 0; uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[s], ph);
@@ -139,14 +139,14 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp & 3;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float* out = p.partial + (size_t)blockIdx.x * p.Kin * p.Nout;
+    float* out = p.partial + (size_t)blockIdx.x * p.Kin * p.Npad;
     for (int mt = 0; mt < mtiles; ++mt) {
       const int row = mt * 128 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < gg; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + c * 32), r);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.Nout + c * 32);
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.Npad + c * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -163,17 +163,20 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
 }
 
-// dW[i] = sum over CTAs (fixed order) of partial[c][i]
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partial, int n_part, int64_t n_vec,
-                                                           float4* __restrict__ out) {
+// dW[r][c] = sum over CTAs (fixed order) of partial[cta][r][c], dropping the padding columns
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ partial, int n_part, int Kin,
+                                                           int Nout, int Npad, float* __restrict__ out) {
+  const int64_t n_vec = (int64_t)Kin * Npad / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vec) return;
+  const int row = (int)(i / (Npad / 4)), c4 = (int)(i % (Npad / 4)) * 4;
+  if (c4 >= Nout) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = 0; c < n_part; ++c) {
     const float4 v = __ldcs(partial + (size_t)c * n_vec + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  out[i] = acc;
+  *reinterpret_cast<float4*>(out + (size_t)row * Nout + c4) = acc;   // Nout % 4 == 0
 }
 
 // [rows, width] fp32 row-major (ld): boxes of 32 columns x 16 rows, 128B swizzle, zero fill past the last row
@@ -196,15 +199,15 @@ using namespace b200gnn;
 
 extern "C" int64_t b200gnn_wgrad_workspace_floats(int64_t Kin, int64_t Nout) {
   if (Kin <= 0 || Nout <= 0) return B200GNN_ERR_BAD_ARG;
-  return 148 * Kin * Nout;
+  return 148 * Kin * ((Nout + 31) / 32 * 32);
 }
 
 extern "C" int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const float* G, int64_t ldg, float* dW,
                                              int64_t Nn, int64_t Kin, int64_t Nout, float* workspace, void* stream) {
   if (!X || !G || !dW || !workspace || Nn <= 0 || Kin <= 0 || Nout <= 0 || ldx < Kin || ldg < Nout || Nn >= INT32_MAX)
     return B200GNN_ERR_BAD_ARG;
-  // tensor-core tiling: Kin in {128, 256}; Nout a multiple of 32 up to 256; TMA alignment
-  if (Kin % 128 || Kin > 256 || Nout % 32 || Nout > 256 || ldx % 4 || ldg % 4 || !aligned_to(X, 16) || !aligned_to(G, 16) ||
+  // tensor-core tiling: Kin in {128, 256}; Nout a multiple of 4 up to 256 (padded to 32 by TMA zero fill); alignment
+  if (Kin % 128 || Kin > 256 || Nout % 4 || Nout > 256 || ldx % 4 || ldg % 4 || !aligned_to(X, 16) || !aligned_to(G, 16) ||
       !aligned_to(dW, 16) || !aligned_to(workspace, 16))
     return B200GNN_ERR_UNSUPPORTED;
   CUtensorMap tX, tG;
@@ -219,6 +222,7 @@ extern "C" int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const 
   cudaStream_t st = (cudaStream_t)stream;
   wgrad::Params p;
   p.partial = workspace; p.Nn = (int32_t)Nn; p.Kin = (int32_t)Kin; p.Nout = (int32_t)Nout;
+  p.Npad = (int32_t)((Nout + 31) / 32 * 32);
   p.num_kb = (int32_t)((Nn + wgrad::BKN - 1) / wgrad::BKN);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -228,8 +232,8 @@ extern "C" int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const 
   int rc;
   wgrad::wgrad_tf32x3_kernel<<<grid, wgrad::THREADS, wgrad::SMEM_BYTES, st>>>(tX, tG, p);
   if ((rc = check_launch())) return rc;
-  const int64_t n_vec = Kin * Nout / 4;
+  const int64_t n_vec = Kin * (int64_t)p.Npad / 4;
   wgrad::wgrad_reduce_kernel<<<(int)((n_vec + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(workspace), grid,
-                                                                        n_vec, reinterpret_cast<float4*>(dW));
+                                                                        (int)Kin, (int)Nout, p.Npad, dW);
   return check_launch();
 }

@@ -279,6 +279,187 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_kernel(const SpmmPa
   else spmm_chunk_cta<V, CH, HAS_VAL, STATS>(p, (int)blockIdx.x - p.n_seg, s_mem);
 }
 
+
+// ------------------------------------------------------------------ pipelined chunk kernel (K = 128*CH floats)
+// Same chunk/row ownership as spmm_chunk_cta, but the neighbour rows of a whole run of consecutive rows are
+// streamed through a per-warp shared-memory ring with cp.async (LDGSTS.128, L1 bypass): each lane copies the
+// 16-byte slices it will later consume itself, so no cross-lane synchronisation is needed, the copies cost no
+// registers, and the pipeline keeps PIPE_BYTES of gather traffic per warp in flight ACROSS row boundaries
+// (the register-staged loop drains at every row end, which is what limits it on graphs of mean degree ~15).
+constexpr int PIPE_BYTES = 8192;                 // ring bytes per warp
+constexpr int PIPE_SMEM = SPMM_WARPS * PIPE_BYTES;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CH, bool HAS_VAL, bool STATS>
+__device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const int cta, float* s_stat, float4* ring_all) {
+  constexpr int D = PIPE_BYTES / (CH * 512);     // ring depth in neighbour rows (CH=2 -> 8, CH=1 -> 16)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* ring = ring_all + (size_t)warp * (PIPE_BYTES / 16);   // slot s: ring[s*CH*32 + j*32 + lane]
+  const float4* Xv = reinterpret_cast<const float4*>(p.X);
+  float4* Yv = reinterpret_cast<float4*>(p.Y);
+  const size_t ldxv = (size_t)(p.ldx / 4), ldyv = (size_t)(p.ldy / 4);
+
+  float4 ssum[CH], ssq[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) { vzero(ssum[j]); vzero(ssq[j]); }
+
+  const int chunk = cta * SPMM_WARPS + warp;
+  const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
+  const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
+
+  auto flush = [&](int row, int deg, float4 (&acc)[CH]) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int voff = lane + 32 * j;
+      float4 y = acc[j];
+      if (p.mean) vdiv(y, (float)max(deg, 1));
+      if (p.bias) vadd(y, load_bias<float4>(p.bias, voff));
+      float4* dst = Yv + (size_t)row * ldyv + voff;
+      if (p.stream_store) vstcs(dst, y); else *dst = y;
+      if (STATS) vstat(ssum[j], ssq[j], y);
+      vzero(acc[j]);
+    }
+  };
+
+  int r = row_lo;
+  while (r < row_hi) {
+    // ---- a run [r, run_end) of consecutive non-hub rows; hub rows belong to the split path
+    int e_lo = __ldg(p.rowptr + r);
+    {
+      const int e_next = __ldg(p.rowptr + r + 1);
+      if (e_next - e_lo > p.hub_threshold) { ++r; continue; }
+    }
+    int run_end = r + 1, e_hi = __ldg(p.rowptr + r + 1);
+    while (run_end < row_hi) {
+      const int nx = __ldg(p.rowptr + run_end + 1);
+      if (nx - e_hi > p.hub_threshold) break;
+      e_hi = nx; ++run_end;
+    }
+    const int n = e_hi - e_lo;
+
+    // row ends of the run, 32 at a time in registers
+    int rbase = r;
+    int rp = (rbase + lane < run_end) ? __ldg(p.rowptr + rbase + lane + 1) : e_hi;
+    auto row_end_of = [&](int row) {
+      if (row - rbase >= 32) {            // warp-uniform
+        rbase = row;
+        rp = (rbase + lane < run_end) ? __ldg(p.rowptr + rbase + lane + 1) : e_hi;
+      }
+      return __shfl_sync(FULL_MASK, rp, row - rbase);
+    };
+
+    float4 acc[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) vzero(acc[j]);
+    int row_beg = e_lo;                    // first edge of row r
+    int rend = row_end_of(r);
+    while (r < run_end && rend == row_beg) {   // leading empty rows
+      flush(r, 0, acc);
+      ++r;
+      if (r < run_end) rend = row_end_of(r);
+    }
+    if (n == 0) continue;
+
+    // two 32-edge windows of (col,val): A = consume batch, B = the next one
+    int cA, cB; float vA, vB;
+    {
+      const int eA = e_lo + lane, eB = e_lo + 32 + lane;
+      cA = eA < e_hi ? __ldg(p.col + eA) : 0;
+      cB = eB < e_hi ? __ldg(p.col + eB) : 0;
+      vA = HAS_VAL ? (eA < e_hi ? __ldg(p.val + eA) : 0.f) : 1.f;
+      vB = HAS_VAL ? (eB < e_hi ? __ldg(p.val + eB) : 0.f) : 1.f;
+    }
+    auto issue = [&](int jj) {             // copy neighbour row of edge jj (relative) into ring slot jj % D
+      if (jj < n) {
+        const int w = jj & 63;             // position inside the 64-edge (A|B) window
+        const int cc = (w < 32) ? __shfl_sync(FULL_MASK, cA, w) : __shfl_sync(FULL_MASK, cB, w - 32);
+        const float4* src = Xv + (size_t)cc * ldxv + lane;
+        float4* dst = ring + (jj % D) * (CH * 32) + lane;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) cp_async16(dst + 32 * j, src + 32 * j);
+      }
+      cp_async_commit();                   // always commit: keeps the group count uniform
+    };
+    // NOTE: window positions are relative to the batch base jb (multiple of 32); issue() is only ever called
+    // with jj in [jb, jb+64), which the D <= 32 look-ahead guarantees.
+#pragma unroll 1
+    for (int i = 0; i < D; ++i) issue(i);
+
+    int jb = 0;                            // base of window A (relative edge index)
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      if (j - jb == 32) {                  // advance the windows: A <- B, B <- next 32 edges
+        jb += 32;
+        cA = cB; vA = vB;
+        const int eB = e_lo + jb + 32 + lane;
+        cB = eB < e_hi ? __ldg(p.col + eB) : 0;
+        vB = HAS_VAL ? (eB < e_hi ? __ldg(p.val + eB) : 0.f) : 1.f;
+      }
+      cp_async_wait<D - 1>();              // the copy of edge j has landed (groups retire in order)
+      const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, j - jb) : 1.f;
+      const float4* slot = ring + (j % D) * (CH * 32) + lane;
+      float4 x[CH];
+#pragma unroll
+      for (int jj = 0; jj < CH; ++jj) x[jj] = slot[32 * jj];
+#pragma unroll
+      for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, x[jj]);
+      // refill the slot just consumed (the loads above have been consumed by the FMAs)
+      {
+        const int jn = j + D;
+        if (jn < n) {
+          const int wpos = jn - jb;        // < 64 because D <= 32
+          const int cc = (wpos < 32) ? __shfl_sync(FULL_MASK, cA, wpos) : __shfl_sync(FULL_MASK, cB, wpos - 32);
+          const float4* src = Xv + (size_t)cc * ldxv + lane;
+          float4* dst = ring + (jn % D) * (CH * 32) + lane;
+#pragma unroll
+          for (int jj = 0; jj < CH; ++jj) cp_async16(dst + 32 * jj, src + 32 * jj);
+        }
+        cp_async_commit();
+      }
+      // row boundaries (also flushes empty rows that follow)
+      const int e_next = e_lo + j + 1;
+      while (r < run_end && rend == e_next) {
+        flush(r, rend - row_beg, acc);
+        row_beg = rend;
+        ++r;
+        if (r < run_end) rend = row_end_of(r);
+      }
+    }
+    cp_async_wait<0>();
+  }
+
+  if (STATS) {
+    float* ss = s_stat;
+    float* sq = s_stat + p.K;
+    for (int i = threadIdx.x; i < 2 * p.K; i += SPMM_THREADS) s_stat[i] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < SPMM_WARPS; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) smem_accum(ss, sq, lane + 32 * j, ssum[j], ssq[j]);
+      }
+      __syncthreads();
+    }
+    float* out = p.stat_partial + (size_t)cta * 2 * p.K;
+    for (int i = threadIdx.x; i < 2 * p.K; i += SPMM_THREADS) out[i] = s_stat[i];
+  }
+}
+
+template <int CH, bool HAS_VAL, bool STATS>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_pipe_kernel(const SpmmParams p) {
+  __shared__ float s_mem[2 * SPMM_MAX_SLAB_FLOATS];
+  extern __shared__ float4 s_ring[];
+  if ((int)blockIdx.x < p.n_seg) spmm_hub_seg_cta<float4, CH, HAS_VAL>(p, (int)blockIdx.x, s_mem);
+  else spmm_chunk_cta_pipe<CH, HAS_VAL, STATS>(p, (int)blockIdx.x - p.n_seg, s_mem, s_ring);
+}
+
 // Sum a hub row's segment partials in segment order, apply the epilogue.
 __global__ void __launch_bounds__(256) spmm_hub_finalize_kernel(const SpmmParams p) {
   const int h = blockIdx.x;
@@ -325,6 +506,34 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   } else {
     if (stats) spmm_rows_kernel<V, CH, false, true><<<grid, SPMM_THREADS, 0, st>>>(p);
     else spmm_rows_kernel<V, CH, false, false><<<grid, SPMM_THREADS, 0, st>>>(p);
+  }
+  if ((rc = check_launch())) return rc;
+  if (p.n_hub > 0) {
+    spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}
+
+template <int CH>
+static int launch_spmm_pipe(const SpmmParams& p, cudaStream_t st) {
+  int rc;
+  const bool stats = p.stat_partial != nullptr;
+  const int grid = p.main_grid + p.n_seg;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+    attr_done = true;
+  }
+  if (p.val) {
+    if (stats) spmm_rows_pipe_kernel<CH, true, true><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
+    else spmm_rows_pipe_kernel<CH, true, false><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
+  } else {
+    if (stats) spmm_rows_pipe_kernel<CH, false, true><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
+    else spmm_rows_pipe_kernel<CH, false, false><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
   }
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
@@ -427,6 +636,10 @@ __global__ void __launch_bounds__(256) chunk_plan_kernel(const int32_t* __restri
 
 using namespace b200gnn;
 
+// 0 = automatic (pipelined kernel where eligible), 1 = always the register-staged kernel (tuning / A-B tests)
+static int g_spmm_variant = 0;
+extern "C" void b200gnn_spmm_set_variant(int v) { g_spmm_variant = v; }
+
 extern "C" int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz, int32_t row_cost) {
   if (n_rows < 0 || nnz < 0 || chunk_nnz <= 0 || row_cost <= 0) return B200GNN_ERR_BAD_ARG;
   const int64_t total = nnz + n_rows * (int64_t)row_cost;
@@ -502,7 +715,15 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   if (!single_slab) p.stat_partial = nullptr;  // stats by a separate pass below
 
   int rc;
-  if (W == 4) rc = dispatch_ch<float4>(p, st);
+  // measured on B200 (ARXIV-shape): the pipelined kernel wins at K=256 (0.29 vs 0.42 ms) and loses slightly at
+  // K=128 (0.26 vs 0.23 ms: per-edge bookkeeping is amortised over half the bytes), so it is used from K=256 up;
+  // variant 2 forces it for K=128 too.
+  const bool pipe_ok = (W == 4) && g_spmm_variant != 1 &&
+                       (p.nvec == 64 || p.nvec == 128 || (p.nvec == 32 && g_spmm_variant == 2));
+  if (pipe_ok && p.nvec == 32) rc = launch_spmm_pipe<1>(p, st);
+  else if (pipe_ok && p.nvec == 64) rc = launch_spmm_pipe<2>(p, st);
+  else if (pipe_ok && p.nvec == 128) rc = launch_spmm_pipe<4>(p, st);
+  else if (W == 4) rc = dispatch_ch<float4>(p, st);
   else if (W == 2) rc = dispatch_ch<float2>(p, st);
   else rc = dispatch_ch<float>(p, st);
   if (rc) return rc;

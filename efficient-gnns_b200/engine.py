@@ -113,7 +113,7 @@ class GCNStudentTrainer:
         self.W_split = [(torch.empty(dims[l], dims[l + 1], device=dev), torch.empty(dims[l], dims[l + 1], device=dev))
                         for l in range(self.L)]
         wg = [ops.wgrad_supported(dims[l], dims[l + 1]) for l in range(self.L)]
-        self.wgrad_ws = (torch.empty(148 * max(dims[l] * dims[l + 1] for l in range(self.L) if wg[l]), device=dev)
+        self.wgrad_ws = (torch.empty(148 * max(dims[l] * ((dims[l + 1] + 31) // 32 * 32) for l in range(self.L) if wg[l]), device=dev)
                          if self.tc_gemm and any(wg) else None)
         self.running_mean = [torch.zeros(d, device=dev) for d in dims[1:-1]]
         self.running_var = [torch.ones(d, device=dev) for d in dims[1:-1]]
@@ -255,8 +255,7 @@ class GCNStudentTrainer:
             torch.mm(d_out, self.W[l].t(), out=d_inp)
 
     def _linear_wgrad(self, l: int, inp: torch.Tensor, d_out: torch.Tensor):
-        """grad W_l = inp^T @ d_out: split-K tcgen05 kernel where the tiling allows, cuBLAS fp32 otherwise
-        (the 256x40 classifier weight: 3.5 GFLOP of the step's ~100)."""
+        """grad W_l = inp^T @ d_out: split-K tcgen05 kernel where the tiling allows, cuBLAS fp32 otherwise."""
         if self.tc_gemm and ops.wgrad_supported(self.dims[l], self.dims[l + 1]):
             ops.gemm_wgrad_tf32x3(inp, d_out, out=self.gW[l], workspace=self.wgrad_ws)
         else:

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200gnn_csr_hub_count": (_int, [_i32p, _i64, _i32, _i32, _i32p, _ptr]),
     "b200gnn_csr_hub_fill": (_int, [_i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _ptr]),
     "b200gnn_spmm_stat_slots": (_i64, [_i64, _i64]),
+    "b200gnn_spmm_set_variant": (None, [_int]),
     "b200gnn_spmm_csr_f32": (_int, [_i32p, _i32p, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _int,
                                     _f32p, _f32p, _i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _i64, _f32p, _ptr]),
     "b200gnn_rows_slots": (_i64, [_i64]),

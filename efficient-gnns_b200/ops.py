@@ -15,6 +15,11 @@ from .sparse import CsrGraph, SparseTensor
 _REDUCE = {"sum": lib.REDUCE_SUM, "add": lib.REDUCE_SUM, "mean": lib.REDUCE_MEAN}
 
 
+def set_spmm_variant(variant: int) -> None:
+    """0 = automatic kernel choice, 1 = force the register-staged SpMM kernel (A/B measurements)."""
+    lib.load().b200gnn_spmm_set_variant(int(variant))
+
+
 def stat_slots(g: CsrGraph) -> int:
     return int(lib.load().b200gnn_spmm_stat_slots(g.n_chunks, g.n_hub))
 
@@ -218,7 +223,7 @@ def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: O
 
 
 def wgrad_supported(k_in: int, n_out: int) -> bool:
-    return k_in in (128, 256) and n_out % 32 == 0 and 0 < n_out <= 256
+    return k_in in (128, 256) and n_out % 4 == 0 and 0 < n_out <= 256
 
 
 def gemm_wgrad_tf32x3(x: torch.Tensor, g: torch.Tensor, out: Optional[torch.Tensor] = None,

@@ -101,6 +101,10 @@ int b200gnn_csr_hub_fill(const int32_t* rowptr, int64_t n_rows,
  * MEAN divides by max(degree,1); empty rows give 0 (+bias).
  * ------------------------------------------------------------------ */
 int64_t b200gnn_spmm_stat_slots(int64_t n_chunks, int64_t n_hub);
+/* Kernel selection for tuning / A-B measurement: 0 = automatic (cp.async-pipelined kernel for K in
+ * {256,512}, register-staged kernel otherwise), 1 = always the register-staged kernel, 2 = pipelined
+ * also for K=128. */
+void b200gnn_spmm_set_variant(int variant);
 int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col,
                          const float* val, const float* X, int64_t ldx,
                          float* Y, int64_t ldy, int64_t n_rows, int64_t n_src,
@@ -208,7 +212,7 @@ int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
 
 /* Weight gradient  dW[Kin,Nout] = X[Nn,Kin]^T * G[Nn,Nout]  (GCNConv weight.grad / nn.Linear weight.grad^T),
  * split-K over the node index on tcgen05 (3xTF32), partials reduced in fixed order.
- * Kin in {128,256}, Nout a multiple of 32 up to 256 (else B200GNN_ERR_UNSUPPORTED: caller keeps the library GEMM).
+ * Kin in {128,256}, Nout a multiple of 4 up to 256 (else B200GNN_ERR_UNSUPPORTED: caller keeps the library GEMM).
  * workspace: float[b200gnn_wgrad_workspace_floats(Kin,Nout)]. */
 int64_t b200gnn_wgrad_workspace_floats(int64_t Kin, int64_t Nout);
 int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const float* G,

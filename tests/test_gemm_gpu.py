@@ -47,7 +47,8 @@ def test_gemm_deterministic_and_reusable():
     assert torch.equal(o1, o2)
 
 
-@pytest.mark.parametrize("Nn,Kin,Nout", [(16, 128, 32), (1000, 128, 256), (5003, 256, 256), (40_000, 256, 64), (7, 128, 128)])
+@pytest.mark.parametrize("Nn,Kin,Nout", [(16, 128, 32), (1000, 128, 256), (5003, 256, 256), (40_000, 256, 64), (7, 128, 128),
+                                          (3000, 256, 40), (999, 128, 4), (2000, 256, 100)])
 def test_wgrad_matches_fp64(Nn, Kin, Nout):
     g = torch.Generator().manual_seed(Nn + Kin + Nout)
     x = torch.randn(Nn, Kin, generator=g)
@@ -63,6 +64,6 @@ def test_wgrad_matches_fp64(Nn, Kin, Nout):
 
 def test_wgrad_unsupported_shapes_are_reported():
     from efficient_gnns_b200 import lib
-    assert not ops.wgrad_supported(256, 40) and ops.wgrad_supported(128, 256)
+    assert not ops.wgrad_supported(64, 40) and ops.wgrad_supported(128, 256) and ops.wgrad_supported(256, 40)
     with pytest.raises(lib.B200GnnError):
-        ops.gemm_wgrad_tf32x3(torch.randn(100, 256, device="cuda"), torch.randn(100, 40, device="cuda"))
+        ops.gemm_wgrad_tf32x3(torch.randn(100, 64, device="cuda"), torch.randn(100, 40, device="cuda"))

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--widths", type=int, nargs="+", default=[256, 128, 40])
     ap.add_argument("--thresholds", type=int, nargs="+", default=[256])
     ap.add_argument("--chunks", type=int, nargs="+", default=[128])
+    ap.add_argument("--variants", type=int, nargs="+", default=[0])
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     S = synthetic.ARXIV
@@ -53,7 +54,9 @@ def main():
     res = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     adjs = {gcn: build_adj(n, S["num_edges"], gcn=gcn) for gcn in (True, False)}
-    for thr in a.thresholds:
+    for variant in a.variants:
+     ops.set_spmm_variant(variant)
+     for thr in a.thresholds:
       for chunk in a.chunks:
         for gcn in (True, False):
             st = adjs[gcn].storage
@@ -69,7 +72,7 @@ def main():
                 med, best = time_fn(lambda: ops.spmm_csr(G, x, red, out=out), a.iters, flush)
                 alg = 2 * n * K * 4 + nnz * (4 + (4 if gcn else 0)) + (n + 1) * 4
                 gather = nnz * (K * 4 + 8) + n * K * 4
-                rec = dict(kernel="spmm", weighted=gcn, reduce=red, K=K, hub_threshold=thr, chunk_nnz=chunk, n_chunks=G.n_chunks, n_hub=G.n_hub, n_seg=G.n_seg,
+                rec = dict(kernel="spmm", variant=variant, weighted=gcn, reduce=red, K=K, hub_threshold=thr, chunk_nnz=chunk, n_chunks=G.n_chunks, n_hub=G.n_hub, n_seg=G.n_seg,
                            nnz=nnz, ms_median=med, ms_best=best, alg_GBps=alg / med / 1e6, gather_GBps=gather / med / 1e6,
                            edges_per_s=nnz / med * 1e3)
                 print(json.dumps(rec), flush=True)
