@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* _
                                                                   const float* __restrict__ shift, int relu, float p,
                                                                   uint64_t seed, uint64_t offset,
                                                                   const int32_t* __restrict__ step_dev,
-                                                                  uint64_t step_mul) {
+                                                                  uint64_t step_mul, uint64_t index_offset) {
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (step_dev) offset += (uint64_t)(*step_dev) * step_mul;  // graph-replayable per-step offset
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* _
     }
     if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
     if (p > 0.f) {
-      const uint4 r = philox4x32(seed, offset, (uint64_t)i);
+      const uint4 r = philox4x32(seed, offset, (uint64_t)i + index_offset);
       y.x = (u32_to_unit(r.x) >= p) ? y.x * inv_keep : 0.f;
       y.y = (u32_to_unit(r.y) >= p) ? y.y * inv_keep : 0.f;
       y.z = (u32_to_unit(r.z) >= p) ? y.z * inv_keep : 0.f;
@@ -227,6 +227,23 @@ __global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_apply_kernel(
 }
 
 // Sum partial[slots][2][K] (first plane only) -> out[K]   (bias gradients)
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial, int slots, int K2,
+                                                             float* __restrict__ out) {
+  __shared__ double sh[FIN_GROUPS][FIN_COLS];
+  const int c = threadIdx.x % FIN_COLS, g = threadIdx.x / FIN_COLS;
+  const int k = blockIdx.x * FIN_COLS + c;
+  double s = 0.0;
+  if (k < K2)
+    for (int j = g; j < slots; j += FIN_GROUPS) s += (double)partial[(size_t)j * K2 + k];
+  sh[g][c] = s;
+  __syncthreads();
+  if (g == 0 && k < K2) {
+    s = 0.0;
+    for (int j = 0; j < FIN_GROUPS; ++j) s += sh[j][c];
+    out[k] = (float)s;
+  }
+}
+
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int slots, int K,
                                                               float* __restrict__ out) {
   double s, q; int k;
@@ -294,14 +311,14 @@ extern "C" int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int6
 extern "C" int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
                                                const float* scale, const float* shift, int relu, float p, uint64_t seed,
                                                uint64_t offset, const int32_t* step_dev, uint64_t step_mul,
-                                               void* stream) {
+                                               uint64_t row_offset, void* stream) {
   if (!rows_ok(n_rows, K) || !Y || !out || p < 0.f || p >= 1.f || ((scale == nullptr) != (shift == nullptr)) ||
       !aligned_to(Y, 16) || !aligned_to(out, 16))
     return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
   const int64_t n_vec = n_rows * (K / 4);
   affine_relu_dropout_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-      Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, seed, offset, step_dev, step_mul);
+      Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, seed, offset, step_dev, step_mul, row_offset * (uint64_t)(K / 4));
   return check_launch();
 }
 
@@ -314,23 +331,36 @@ extern "C" int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K,
   return check_launch();
 }
 
-extern "C" int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
-                                      const float* invstd, const float* gamma, int64_t n_rows, int64_t K, float p,
-                                      float* dY, float* dgamma, float* dbeta, float* dbias, float* partial,
-                                      int64_t slots, float* coef, void* stream) {
-  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Xout || !Y || !mean || !invstd || !gamma || !dY || !dgamma ||
-      !dbeta || !partial || !coef || slots < 1 || p < 0.f || p >= 1.f)
+// phase 1: partial[slots][2][K] = per-slot column sums of dz and dz*xhat
+extern "C" int b200gnn_bn_act_bwd_reduce_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
+                                             const float* invstd, int64_t n_rows, int64_t K, float p, float* partial,
+                                             int64_t slots, void* stream) {
+  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Xout || !Y || !mean || !invstd || !partial || slots < 1 ||
+      p < 0.f || p >= 1.f)
     return B200GNN_ERR_BAD_ARG;
   if (ROWS_THREADS / (K / 4) < 1) return B200GNN_ERR_UNSUPPORTED;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  bn_act_bwd_reduce_kernel<<<(int)slots, ROWS_THREADS, 2 * K * sizeof(float), (cudaStream_t)stream>>>(
+      dOut, Xout, Y, mean, invstd, n_rows, (int)K, inv_keep, partial, (int)slots);
+  return check_launch();
+}
+
+// phase 2: sums[sum_slots][2][K] (local partials, or one slot of globally reduced sums) + the normalisation count
+// n_norm (global row count) -> dgamma, dbeta, dY (and dbias = column sums of the LOCAL dY rows if requested)
+extern "C" int b200gnn_bn_act_bwd_apply_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
+                                            const float* invstd, const float* gamma, const float* sums,
+                                            int64_t sum_slots, int64_t n_norm, int64_t n_rows, int64_t K, float p,
+                                            float* dY, float* dgamma, float* dbeta, float* dbias, float* partial,
+                                            int64_t slots, float* coef, void* stream) {
+  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Xout || !Y || !mean || !invstd || !gamma || !sums || !dY ||
+      !dgamma || !dbeta || !partial || !coef || slots < 1 || sum_slots < 1 || n_norm < 1 || p < 0.f || p >= 1.f)
+    return B200GNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const size_t smem = 2 * K * sizeof(float);
   int rc;
-  bn_act_bwd_reduce_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, n_rows, (int)K, inv_keep,
-                                                                  partial, (int)slots);
-  if ((rc = check_launch())) return rc;
-  bn_bwd_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(partial, (int)slots, (int)K, n_rows, gamma, invstd, dgamma,
-                                                              dbeta, coef);
+  bn_bwd_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(sums, (int)sum_slots, (int)K, n_norm, gamma,
+                                                                              invstd, dgamma, dbeta, coef);
   if ((rc = check_launch())) return rc;
   bn_act_bwd_apply_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, coef, n_rows, (int)K,
                                                                  inv_keep, dY, dbias ? partial : nullptr, (int)slots);
@@ -340,6 +370,24 @@ extern "C" int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, cons
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
+}
+
+extern "C" int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
+                                      const float* invstd, const float* gamma, int64_t n_rows, int64_t K, float p,
+                                      float* dY, float* dgamma, float* dbeta, float* dbias, float* partial,
+                                      int64_t slots, float* coef, void* stream) {
+  int rc = b200gnn_bn_act_bwd_reduce_f32(dOut, Xout, Y, mean, invstd, n_rows, K, p, partial, slots, stream);
+  if (rc) return rc;
+  return b200gnn_bn_act_bwd_apply_f32(dOut, Xout, Y, mean, invstd, gamma, partial, slots, n_rows, n_rows, K, p, dY,
+                                      dgamma, dbeta, dbias, partial, slots, coef, stream);
+}
+
+// out[2K] = sum over slots of partial[slot][2K]  (fp64 accumulation; used before a cross-rank all-reduce)
+extern "C" int b200gnn_partial_reduce_f32(const float* partial, int64_t slots, int64_t K2, float* out, void* stream) {
+  if (!partial || !out || slots < 1 || K2 < 1) return B200GNN_ERR_BAD_ARG;
+  partial_reduce_kernel<<<(int)((K2 + FIN_COLS - 1) / FIN_COLS), 256, 0, (cudaStream_t)stream>>>(partial, (int)slots, (int)K2,
+                                                                                               out);
+  return check_launch();
 }
 
 extern "C" int b200gnn_col_sum_f32(const float* Y, int64_t n_rows, int64_t K, float* out, float* partial,

@@ -121,22 +121,23 @@ extern "C" int64_t b200gnn_kd_partials(int64_t n_train) {
 
 extern "C" int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld, const int64_t* train_idx, int64_t n_train,
                                            const int64_t* labels, const float* teacher_logits, int64_t ldt, int64_t C,
-                                           float alpha, float T, float* dlogits, int64_t ldd, float* loss_out,
-                                           float* partial, void* stream) {
-  if (!logits || !labels || !dlogits || !loss_out || !partial || n_train <= 0 || C <= 0 || ld < C || ldd < C)
+                                           float alpha, float T, int64_t n_norm, float* dlogits, int64_t ldd,
+                                           float* loss_out, float* partial, void* stream) {
+  if (!logits || !labels || !dlogits || !loss_out || !partial || n_train < 0 || C <= 0 || ld < C || ldd < C)
     return B200GNN_ERR_BAD_ARG;
   if (C > 32 * LOSS_MAX_PER_LANE) return B200GNN_ERR_UNSUPPORTED;
   if (teacher_logits && (ldt < C || T <= 0.f)) return B200GNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)b200gnn_kd_partials(n_train);
   const bool kd = teacher_logits != nullptr;
-  const float w_cls = (kd ? (1.f - alpha) : 1.f) / (float)n_train;
-  const float w_kd = kd ? alpha * T * T / ((float)n_train * (float)C) : 0.f;
+  if (n_norm <= 0) n_norm = n_train;   // sharded runs normalise by the GLOBAL number of training rows
+  const float w_cls = (kd ? (1.f - alpha) : 1.f) / (float)n_norm;
+  const float w_kd = kd ? alpha * T * T / ((float)n_norm * (float)C) : 0.f;
   int rc;
   kd_rows_kernel<<<grid, LOSS_THREADS, 0, st>>>(logits, ld, train_idx, n_train, labels, teacher_logits, ldt, (int)C,
                                                 kd ? 1.f / T : 1.f, w_cls, w_kd, dlogits, ldd, partial);
   if ((rc = check_launch())) return rc;
-  kd_finalize_kernel<<<1, 256, 0, st>>>(partial, grid, 1.f / (float)n_train, 1.f / ((float)n_train * (float)C), alpha, T,
+  kd_finalize_kernel<<<1, 256, 0, st>>>(partial, grid, 1.f / (float)n_norm, 1.f / ((float)n_norm * (float)C), alpha, T,
                                       kd ? 1 : 0, loss_out);
   return check_launch();
 }

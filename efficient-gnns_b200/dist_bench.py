@@ -1,0 +1,113 @@
+"""bench.py's N>1 arm: the same GCN + logit-KD training step, node-parallel over N GPUs (torchrun, one rank per GPU)."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def run(args):
+    import bench as B
+    from . import lib, sparse, synthetic
+    from .dist import ShardedGCNTrainer
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    ds = synthetic.make_node_dataset(synthetic.ARXIV, seed=0)
+    n = ds.num_nodes
+    ei = ds.edge_index.to(dev)
+    perm = (ei[1] * n + ei[0]).argsort()
+    adj = sparse.SparseTensor(row=ei[1][perm], col=ei[0][perm], sparse_sizes=(n, n), is_sorted=True).to_symmetric()
+    tr = ShardedGCNTrainer(adj, B.DIMS, dropout=0.5, lr=0.01, seed=0)
+    nnz_global = torch.tensor([tr.nnz], device=dev, dtype=torch.long)
+    dist.all_reduce(nnz_global)
+    nnz = int(nnz_global.item())
+    x_pad, y_loc, tr_loc, t_loc = tr.shard_inputs(ds.x, ds.y.squeeze(1), ds.split_idx["train"], ds.teacher_logits)
+
+    graph = None
+    for _ in range(2):
+        tr.train_step(x_pad, y_loc, tr_loc, t_loc)
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        try:   # NCCL collectives are capturable; fall back to eager launches if this build refuses
+            tr.capture(x_pad, y_loc, tr_loc, t_loc, warmup=1)
+            graph = True
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[dist_bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager", flush=True)
+            graph = None
+            torch.cuda.synchronize()
+    step = tr.replay if graph else (lambda: tr.train_step(x_pad, y_loc, tr_loc, t_loc))
+    lib.reset_launch_count()
+    tr.train_step(x_pad, y_loc, tr_loc, t_loc)
+    launches = lib.launch_count()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with B.ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+
+    # end to end: every step re-uploads this rank's inputs from pinned host memory and reads the loss back
+    host = {"x": x_pad.cpu().pin_memory(), "y": y_loc.cpu().pin_memory(), "t": t_loc.cpu().pin_memory(),
+            "i": tr_loc.cpu().pin_memory()}
+    devb = {"x": x_pad, "y": y_loc, "t": t_loc, "i": tr_loc}
+    loss_host = torch.empty(3).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        for k in devb:
+            devb[k].copy_(host[k], non_blocking=True)
+        step()
+        loss_host.copy_(tr.loss_out, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(); torch.cuda.synchronize(); dist.barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+
+    if rank == 0:
+        peak, peak_src = B.peaks()
+        ex = tr.exchange_bytes_per_step()
+        line = {"metric": B.METRIC, "value": 6 * nnz / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": B.workload_config(ds, nnz, {
+                    "parallelism": f"node-parallel x{world}: degree-balanced row blocks, one NCCL all-gather per aggregation",
+                    "cuda_graph": bool(graph), "exchange_bytes_received_per_rank_per_step": ex,
+                    "nvlink_floor_ms": ex / 770e9 * 1e3,
+                    "aggregations_executed": tr.aggregations_per_step()}),
+                "roofline": {"bound": "nvlink+hbm", "note": "multi-GPU point: the all-gathers bound the step; see "
+                             "nvlink_floor_ms (bytes received per rank / 770 GB/s measured peer bandwidth)",
+                             "achieved": ex / (ms_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
+                             "frac": ex / (ms_step * 1e-3) / 1e9 / 770.0, "traffic": None},
+                "cpu_baseline": None,
+                "e2e": {"value": 6 * nnz / (ms_e2e * 1e-3), "unit": B.UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 12 * world},
+                "gpu_launches": launches * args.steps * world, "gpu_launches_per_step_per_rank": launches,
+                "clocks": clk.summary(), "loss": tr.loss_out.tolist()}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -52,7 +52,8 @@ class GCNStudentTrainer:
 
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
                  alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
-                 aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True):
+                 aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True,
+                 _prebuilt_graph: Optional[CsrGraph] = None, _rows_alloc: Optional[int] = None):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         self.device = adj.device
         self.dims, self.L = list(dims), len(dims) - 1
@@ -71,9 +72,13 @@ class GCNStudentTrainer:
         if self.L < 2:
             self.agg_first = False
 
-        norm = gcn_norm(adj)                     # cached=True semantics: normalise once (arxiv_pyg/gnn.py:28)
-        self.G: CsrGraph = norm.storage.engine_csr()
-        self.Gt: CsrGraph = self.G if _is_symmetric(norm) else norm.storage.engine_csc("value")
+        if _prebuilt_graph is not None:          # a row shard of the normalised adjacency (dist.ShardedGCNTrainer)
+            self.G = self.Gt = _prebuilt_graph
+            self.N = _prebuilt_graph.n_rows
+        else:
+            norm = gcn_norm(adj)                 # cached=True semantics: normalise once (arxiv_pyg/gnn.py:28)
+            self.G: CsrGraph = norm.storage.engine_csr()
+            self.Gt: CsrGraph = self.G if _is_symmetric(norm) else norm.storage.engine_csc("value")
         self.nnz = self.G.nnz
 
         # ---- flat parameters: per layer W [in,out], b [out]; per hidden layer gamma, beta
@@ -121,7 +126,13 @@ class GCNStudentTrainer:
 
         # ---- activations / gradients (preallocated; CUDA-graph friendly)
         N = self.N
-        buf = lambda k: torch.empty(N, k, device=dev)  # noqa: E731
+        rows_alloc = N if _rows_alloc is None else _rows_alloc   # shards over-allocate to the common block size
+        self._blocks = []
+
+        def buf(k):
+            blk = torch.zeros(rows_alloc, k, device=dev)
+            self._blocks.append(blk)
+            return blk[:N]
         self.H = [buf(dims[l + 1]) for l in range(self.L)]            # X W
         self.Y = [buf(dims[l + 1]) for l in range(self.L)]            # Â H + b  (last = logits)
         self.A = [buf(dims[l + 1]) for l in range(self.L - 1)]        # dropout(relu(BN(Y)))

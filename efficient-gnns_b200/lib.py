@@ -47,14 +47,18 @@ SIGNATURES = {
     "b200gnn_bn_finalize_f32": (_int, [_f32p, _i64, _i64, _i64, _f32p, _f32p, _f32, _f32, _f32p, _f32p,
                                        _f32p, _f32p, _f32p, _f32p, _ptr]),
     "b200gnn_affine_relu_dropout_f32": (_int, [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _int, _f32, _u64, _u64,
-                                               _i32p, _u64, _ptr]),
+                                               _i32p, _u64, _u64, _ptr]),
     "b200gnn_dropout_mask_u8": (_int, [_ptr, _i64, _i64, _f32, _u64, _u64, _ptr]),
     "b200gnn_bn_act_bwd_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _f32, _f32p, _f32p,
                                       _f32p, _f32p, _f32p, _i64, _f32p, _ptr]),
+    "b200gnn_bn_act_bwd_reduce_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _f32, _f32p, _i64, _ptr]),
+    "b200gnn_bn_act_bwd_apply_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _f32,
+                                            _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _f32p, _ptr]),
+    "b200gnn_partial_reduce_f32": (_int, [_f32p, _i64, _i64, _f32p, _ptr]),
     "b200gnn_adam_step_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _i64, _f32, _f32, _f32, _f32, _i32p, _ptr]),
     "b200gnn_kd_partials": (_i64, [_i64]),
-    "b200gnn_kd_loss_fwd_bwd_f32": (_int, [_f32p, _i64, _ptr, _i64, _ptr, _f32p, _i64, _i64, _f32, _f32, _f32p, _i64,
-                                           _f32p, _f32p, _ptr]),
+    "b200gnn_kd_loss_fwd_bwd_f32": (_int, [_f32p, _i64, _ptr, _i64, _ptr, _f32p, _i64, _i64, _f32, _f32, _i64, _f32p,
+                                           _i64, _f32p, _f32p, _ptr]),
     "b200gnn_split_tf32_f32": (_int, [_f32p, _i64, _i64, _int, _f32p, _f32p, _ptr]),
     "b200gnn_gemm_tf32x3_f32": (_int, [_f32p, _i64, _f32p, _f32p, _i64, _f32p, _i64, _i64, _i64, _i64, _f32p, _ptr]),
     "b200gnn_wgrad_workspace_floats": (_i64, [_i64, _i64]),

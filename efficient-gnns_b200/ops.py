@@ -129,13 +129,13 @@ def bn_finalize(partial: torch.Tensor, n_rows: int, gamma, beta, eps: float = 1e
 
 def affine_relu_dropout(y: torch.Tensor, scale=None, shift=None, relu: bool = True, p: float = 0.0, seed: int = 0,
                         offset: int = 0, out: Optional[torch.Tensor] = None, step_dev: Optional[torch.Tensor] = None,
-                        step_mul: int = 0) -> torch.Tensor:
+                        step_mul: int = 0, row_offset: int = 0) -> torch.Tensor:
     n, K = y.shape
     if out is None:
         out = torch.empty_like(y)
     lib.check(lib.load().b200gnn_affine_relu_dropout_f32(
         _f32(y, "y"), _f32(out, "out"), n, K, _f32(scale, "scale"), _f32(shift, "shift"), int(relu), p, seed, offset,
-        lib.dptr(step_dev, torch.int32, "step_dev"), step_mul, lib.stream_ptr()), "affine_relu_dropout_f32")
+        lib.dptr(step_dev, torch.int32, "step_dev"), step_mul, row_offset, lib.stream_ptr()), "affine_relu_dropout_f32")
     return out
 
 
@@ -176,7 +176,7 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step: torch.Tensor, lr: float,
 
 
 def kd_loss_fwd_bwd(logits, labels, train_idx, teacher_logits=None, alpha: float = 0.9, T: float = 4.0,
-                    d_logits=None, loss_out=None, partial=None):
+                    d_logits=None, loss_out=None, partial=None, n_norm: int = 0):
     """Fused CE / logit-KD over rows train_idx of FULL [N,C] matrices; returns (loss_out[3], d_logits [N,C])."""
     N, C = logits.shape
     n_train = train_idx.numel() if train_idx is not None else N
@@ -186,11 +186,11 @@ def kd_loss_fwd_bwd(logits, labels, train_idx, teacher_logits=None, alpha: float
     if loss_out is None:
         loss_out = torch.empty(3, dtype=torch.float32, device=logits.device)
     if partial is None:
-        partial = torch.empty(2 * int(L.b200gnn_kd_partials(n_train)), dtype=torch.float32, device=logits.device)
+        partial = torch.empty(2 * int(L.b200gnn_kd_partials(max(n_train, 1))), dtype=torch.float32, device=logits.device)
     lib.check(L.b200gnn_kd_loss_fwd_bwd_f32(
         _f32(logits, "logits"), logits.stride(0), lib.dptr(train_idx, torch.int64, "train_idx"), n_train,
         lib.dptr(labels, torch.int64, "labels"), _f32(teacher_logits, "teacher_logits"),
-        teacher_logits.stride(0) if teacher_logits is not None else 0, C, alpha, T, _f32(d_logits, "d_logits"),
+        teacher_logits.stride(0) if teacher_logits is not None else 0, C, alpha, T, n_norm, _f32(d_logits, "d_logits"),
         d_logits.stride(0), _f32(loss_out, "loss_out"), _f32(partial, "partial"), lib.stream_ptr()), "kd_loss_fwd_bwd_f32")
     return loss_out, d_logits
 
@@ -241,3 +241,34 @@ def gemm_wgrad_tf32x3(x: torch.Tensor, g: torch.Tensor, out: Optional[torch.Tens
                                               k_in, n_out, _f32(workspace, "workspace"), lib.stream_ptr()),
               "gemm_wgrad_tf32x3_f32")
     return out
+
+
+def partial_reduce(partial: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[slots, 2, K] (or [slots, K2]) partial sums -> [2, K] / [K2] totals (before a cross-rank all-reduce)."""
+    slots = partial.shape[0]
+    k2 = partial.numel() // slots
+    if out is None:
+        out = torch.empty(partial.shape[1:], dtype=torch.float32, device=partial.device)
+    lib.check(lib.load().b200gnn_partial_reduce_f32(_f32(partial, "partial"), slots, k2, _f32(out, "out"), lib.stream_ptr()),
+              "partial_reduce_f32")
+    return out
+
+
+def bn_act_bwd_reduce(d_out, x_out, y, mean, invstd, p: float, partial: torch.Tensor) -> torch.Tensor:
+    n, K = y.shape
+    lib.check(lib.load().b200gnn_bn_act_bwd_reduce_f32(_f32(d_out, "d_out"), _f32(x_out, "x_out"), _f32(y, "y"),
+                                                       _f32(mean, "mean"), _f32(invstd, "invstd"), n, K, p,
+                                                       _f32(partial, "partial"), partial.shape[0], lib.stream_ptr()),
+              "bn_act_bwd_reduce_f32")
+    return partial
+
+
+def bn_act_bwd_apply(d_out, x_out, y, mean, invstd, gamma, sums, n_norm: int, p: float, d_y, d_gamma, d_beta, d_bias,
+                     partial, coef):
+    n, K = y.shape
+    sum_slots = sums.numel() // (2 * K)
+    lib.check(lib.load().b200gnn_bn_act_bwd_apply_f32(
+        _f32(d_out, "d_out"), _f32(x_out, "x_out"), _f32(y, "y"), _f32(mean, "mean"), _f32(invstd, "invstd"),
+        _f32(gamma, "gamma"), _f32(sums, "sums"), sum_slots, n_norm, n, K, p, _f32(d_y, "d_y"), _f32(d_gamma, "d_gamma"),
+        _f32(d_beta, "d_beta"), _f32(d_bias, "d_bias"), _f32(partial, "partial"), partial.shape[0], _f32(coef, "coef"),
+        lib.stream_ptr()), "bn_act_bwd_apply_f32")

@@ -146,13 +146,15 @@ int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int64_t K,
  *     effective offset = offset + (step_dev ? *step_dev * step_mul : 0),
  * step_dev being a device int32 (e.g. the Adam step counter) so a captured
  * CUDA graph draws a fresh mask on every replay;
+ * row_offset: global index of row 0 of Y (node-parallel shards draw the mask
+ * of their own rows of the global matrix; 0 on a single GPU);
  * b200gnn_dropout_mask_u8 materialises the mask of a given effective offset. */
 int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows,
                                     int64_t K, const float* scale,
                                     const float* shift, int relu, float p,
                                     uint64_t seed, uint64_t offset,
                                     const int32_t* step_dev, uint64_t step_mul,
-                                    void* stream);
+                                    uint64_t row_offset, void* stream);
 int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p,
                             uint64_t seed, uint64_t offset, void* stream);
 /* Backward of out = dropout_p(relu(BN_train(Y))): given dOut, out (for the
@@ -165,6 +167,26 @@ int b200gnn_bn_act_bwd_f32(const float* dOut, const float* Xout, const float* Y,
                            float p, float* dY, float* dgamma, float* dbeta,
                            float* dbias, float* partial, int64_t slots,
                            float* coef, void* stream);
+/* The same backward in two phases, for node-parallel runs that all-reduce the
+ * column sums between them: reduce -> partial[slots][2][K];  apply consumes
+ * `sums[sum_slots][2][K]` (the local partials, or ONE slot of cross-rank sums)
+ * with n_norm = global row count. */
+int b200gnn_bn_act_bwd_reduce_f32(const float* dOut, const float* Xout,
+                                  const float* Y, const float* mean,
+                                  const float* invstd, int64_t n_rows,
+                                  int64_t K, float p, float* partial,
+                                  int64_t slots, void* stream);
+int b200gnn_bn_act_bwd_apply_f32(const float* dOut, const float* Xout,
+                                 const float* Y, const float* mean,
+                                 const float* invstd, const float* gamma,
+                                 const float* sums, int64_t sum_slots,
+                                 int64_t n_norm, int64_t n_rows, int64_t K,
+                                 float p, float* dY, float* dgamma,
+                                 float* dbeta, float* dbias, float* partial,
+                                 int64_t slots, float* coef, void* stream);
+/* out[K2] = sum over slots of partial[slot][K2] (K2 = 2*K for statistics) */
+int b200gnn_partial_reduce_f32(const float* partial, int64_t slots, int64_t K2,
+                               float* out, void* stream);
 /* torch.optim.Adam (defaults: no amsgrad, no weight decay) over flat buffers;
  * *step (device int32) is the number of steps already taken and is incremented
  * (arxiv_pyg/gnn.py:192-193, 308-315). */
@@ -181,6 +203,8 @@ int b200gnn_adam_step_f32(float* params, const float* grads, float* exp_avg,
  * train_idx (int64[n_train], NULL => rows 0..n_train-1) selects the rows, labels is the
  * full int64[N] vector.  dlogits rows in train_idx receive d loss / d logits; the caller
  * zeroes the other rows.  loss_out[3] = {loss, loss_cls, loss_kd}.
+ * n_norm: row count the means are taken over (0 => n_train; node-parallel
+ * shards pass the GLOBAL number of training rows and sum loss_out across ranks).
  * partial: float[2*b200gnn_kd_partials(n_train)] scratch.  C <= 256.
  * ------------------------------------------------------------------ */
 int64_t b200gnn_kd_partials(int64_t n_train);
@@ -189,8 +213,8 @@ int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld,
                                 const int64_t* labels,
                                 const float* teacher_logits, int64_t ldt,
                                 int64_t C, float alpha, float T,
-                                float* dlogits, int64_t ldd, float* loss_out,
-                                float* partial, void* stream);
+                                int64_t n_norm, float* dlogits, int64_t ldd,
+                                float* loss_out, float* partial, void* stream);
 
 /* ------------------------------------------------------------------ *
  * fp32-faithful dense GEMM on tcgen05 tensor cores (3xTF32 split, fp32
