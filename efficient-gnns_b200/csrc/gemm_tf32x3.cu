@@ -5,8 +5,8 @@
 // The reference computes its dense contractions (GCNConv's X·W, nn.Linear, the backward dX = dY·W^T;
 // arxiv_pyg/gnn.py:47,52 via PyG) in fp32 and the parity bar is 1e-5, which a single TF32 pass (10-bit
 // mantissa) cannot meet.  So every product is evaluated with the 3xTF32 split
-//        a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo ,   x_hi = x with the low 13 mantissa bits cleared,
-//                                                    x_lo = (x - x_hi) with the low 13 bits cleared,
+//        a·b ≈ a_hi·b_hi + a_lo·b_hi + a_hi·b_lo ,   x_hi = x rounded to tf32 (cvt.rna),
+//                                                    x_lo = (x - x_hi) rounded to tf32,
 // three tcgen05.mma.kind::tf32 instructions per K-step into the same TMEM accumulator.  The dropped terms
 // are O(2^-22) relative.  B (the small weight matrix) arrives pre-split from b200gnn_split_tf32_f32; A (the
 // big activation matrix) is split on the fly in shared memory, so HBM only ever sees one fp32 copy of it.
@@ -219,9 +219,8 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   const int64_t n = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
-    const uint32_t v = __float_as_uint(W[i]);
-    const uint32_t h = v & TF32_MASK;
-    const uint32_t l = __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) & TF32_MASK;
+    uint32_t h, l;
+    split1(__float_as_uint(W[i]), h, l);
     const int64_t o = transpose ? c * rows + r : i;
     hi[o] = __uint_as_float(h);
     lo[o] = __uint_as_float(l);

@@ -75,13 +75,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 
-// x -> (hi, lo) with hi = x truncated to tf32, lo = (x - hi) truncated to tf32 (both exactly representable)
+// x -> (hi, lo): hi = x ROUNDED to tf32 (cvt.rna: nearest, ties away), lo = (x - hi) rounded to tf32.
+// x - hi is exact in fp32, so hi + lo reproduces x to ~2^-22 relative with a ZERO-MEAN error.  (Truncating instead
+// of rounding leaves every product biased towards zero by ~5e-7; the bias survives the long, heavily cancelling
+// sums of the backward pass and showed up as 1e-4-level errors in the early-layer weight gradients.)
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split1(uint32_t v, uint32_t& h, uint32_t& l) {
+  h = rna_tf32(__uint_as_float(v));
+  l = rna_tf32(__uint_as_float(v) - __uint_as_float(h));
+}
 __device__ __forceinline__ void split4(const uint4& v, uint4& h, uint4& l) {
-  h.x = v.x & TF32_MASK; h.y = v.y & TF32_MASK; h.z = v.z & TF32_MASK; h.w = v.w & TF32_MASK;
-  l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & TF32_MASK;
-  l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & TF32_MASK;
-  l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & TF32_MASK;
-  l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & TF32_MASK;
+  split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -109,5 +109,8 @@ def run(args):
                 "gpu_launches": launches * args.steps * world, "gpu_launches_per_step_per_rank": launches,
                 "clocks": clk.summary(), "loss": tr.loss_out.tolist()}
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    # NCCL teardown with live CUDA graphs that captured collectives can dead-lock; results are out, leave hard.
+    torch.cuda.synchronize()
+    import sys
+    sys.stdout.flush()
+    os._exit(0)

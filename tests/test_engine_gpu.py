@@ -142,3 +142,29 @@ def test_eval_forward_uses_running_statistics():
             h = (h - sd[f"bns.{l}.running_mean"]) / torch.sqrt(sd[f"bns.{l}.running_var"] + 1e-5) * sd[f"bns.{l}.weight"] + sd[f"bns.{l}.bias"]
             h = torch.relu(h)
     assert rel_err(logits, h) < 1e-5
+
+
+def test_sharded_trainer_world1_matches_plain_engine():
+    """The node-parallel code path (relabelling, row-shard CSR, all-gather / all-reduce plumbing, two-phase BatchNorm
+    backward) on a 1-rank NCCL group must reproduce the plain engine; multi-rank equivalence is tests/dist_equiv.py."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from efficient_gnns_b200.dist import ShardedGCNTrainer
+    if not dist.is_initialized():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    tr, rc, x, y, t, idx = build(p=0.0, seed=4)
+    n = x.shape[0]
+    adj = SparseTensor(row=torch.from_numpy(rc[0]).cuda(), col=torch.from_numpy(rc[1]).cuda(), sparse_sizes=(n, n), is_sorted=True)
+    sh = ShardedGCNTrainer(adj, tr.dims, dropout=0.0, seed=4)
+    xc, yc, tc, ic = x.cuda(), y.cuda(), t.cuda(), idx.cuda()
+    l_ref = tr.train_step(xc, yc, ic, tc).clone()
+    l_sh = sh.train_step(*sh.shard_inputs(xc, yc, ic, tc)).clone()
+    assert rel_err(sh.gather_rows(sh.Y[-1]), tr.Y[-1]) < 1e-5
+    assert ((l_sh - l_ref).abs() / l_ref.abs()).max().item() < 1e-5
+    for l in range(tr.L):
+        assert ((sh.gW[l] - tr.gW[l]).norm() / tr.gW[l].norm()).item() < 2e-3
+    assert sh.exchange_bytes_per_step() == 0
