@@ -1,0 +1,362 @@
+"""Drop-in for the reference's ``criterion.py`` (arxiv_pyg/criterion.py:8-149; same copies in mag_pyg/, ppi_pyg/).
+
+Same function names, argument order and return convention ``(loss, loss_cls, loss_aux)``; every loss is computed
+by b200gnn kernels (fused row losses, edge-list passes, tcgen05 3xTF32 GEMMs for the S x S contractions) and is
+differentiable through small ``torch.autograd.Function`` wrappers.  ``from efficient_gnns_b200.criterion import *``
+in place of ``from criterion import *`` is the whole integration.
+
+Sampling (``max_samples``) draws from numpy's global RNG exactly like the reference (criterion.py:63,135) so that a
+seeded run selects the same rows; ``sampled_inds=`` lets tests inject the draw.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import lib, ops
+
+__all__ = ["kd_criterion", "fitnet_criterion", "at_criterion", "gpw_criterion", "lpw_criterion", "nce_criterion"]
+
+_KERNELS = {"cosine": 0, "poly": 1, "l2": 2, "rbf": 3}
+_NORM_EPS = 1e-12  # F.normalize default
+
+
+def _L():
+    return lib.load()
+
+
+def _f32(t, name):
+    return lib.dptr(t, torch.float32, name)
+
+
+def _new(*shape, like):
+    return torch.empty(*shape, dtype=torch.float32, device=like.device)
+
+
+# ----------------------------------------------------------------------------------------- CE / logit KD
+class _RowLoss(torch.autograd.Function):
+    """CE (teacher None) or the fused Hinton KD loss over all rows of logits [n,C]; grad w.r.t. logits only."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, teacher, alpha, T):
+        logits = logits.contiguous()
+        out, d_logits = ops.kd_loss_fwd_bwd(logits, labels.contiguous(), None,
+                                            None if teacher is None else teacher.contiguous(), alpha, T)
+        ctx.save_for_backward(d_logits)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_all):
+        (d_logits,) = ctx.saved_tensors
+        return d_logits * g_loss, None, None, None, None
+
+
+def cross_entropy(logits, labels):
+    return _RowLoss.apply(logits, labels, None, 0.0, 1.0)[0]
+
+
+def kd_criterion(logits, labels, teacher_logits, alpha=0.9, T=4):
+    """criterion.py:8-21."""
+    loss, parts = _RowLoss.apply(logits, labels, teacher_logits, float(alpha), float(T))
+    return loss, parts[1], parts[2]
+
+
+# ----------------------------------------------------------------------------------------- row helpers
+def _normalize(x, scale: float = 1.0):
+    n, F = x.shape
+    out, norm = torch.empty_like(x), _new(n, like=x)
+    lib.check(_L().b200gnn_row_normalize_fwd_f32(_f32(x, "x"), n, F, _NORM_EPS, scale, _f32(out, "out"), _f32(norm, "norm"),
+                                                lib.stream_ptr()), "row_normalize_fwd_f32")
+    return out, norm
+
+
+def _normalize_bwd(out, norm, d_out, scale: float = 1.0):
+    n, F = out.shape
+    d_x = torch.empty_like(out)
+    lib.check(_L().b200gnn_row_normalize_bwd_f32(_f32(out, "out"), _f32(norm, "norm"), _f32(d_out.contiguous(), "d_out"), n, F,
+                                                _NORM_EPS, scale, _f32(d_x, "d_x"), 0, lib.stream_ptr()),
+              "row_normalize_bwd_f32")
+    return d_x
+
+
+def _mse(a, b, want_grad: bool = True):
+    """(loss[1], d_a) with d_a = d mse / d a."""
+    n = a.numel()
+    loss = _new(1, like=a)
+    d_a = torch.empty_like(a) if want_grad else None
+    part = _new(int(_L().b200gnn_reduce_slots(n)), like=a)
+    lib.check(_L().b200gnn_mse_fwd_bwd_f32(_f32(a, "a"), _f32(b, "b"), n, 1.0, _f32(d_a, "d_a"), _f32(loss, "loss"),
+                                          _f32(part, "partial"), lib.stream_ptr()), "mse_fwd_bwd_f32")
+    return loss, d_a
+
+
+def _gemm_nt(a, b):
+    """a[M,K] @ b[N,K]^T on the tensor cores with fp32 fidelity."""
+    hi, lo = ops.split_tf32(b.contiguous())
+    return ops.gemm_tf32x3(a.contiguous(), hi, lo)
+
+
+def _gemm_nn(a, b):
+    """a[M,K] @ b[K,N]."""
+    hi, lo = ops.split_tf32(b.contiguous(), transpose=True)
+    return ops.gemm_tf32x3(a.contiguous(), hi, lo)
+
+
+def _sample(n: int, max_samples: int, device, sampled_inds=None):
+    if max_samples >= n:
+        return None
+    if sampled_inds is None:
+        sampled_inds = np.random.choice(n, max_samples, replace=False)      # reference: criterion.py:63,135
+    return torch.as_tensor(sampled_inds, dtype=torch.long, device=device)
+
+
+# ----------------------------------------------------------------------------------------- FitNet / AT
+class _NormalizedMSE(torch.autograd.Function):
+    """mse(normalize(a), normalize(b)) — fitnet_criterion's auxiliary term (criterion.py:30-33)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        an, na = _normalize(a)
+        bn, nb = _normalize(b)
+        loss, d_an = _mse(an, bn)
+        ctx.save_for_backward(an, na, bn, nb, d_an)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        an, na, bn, nb, d_an = ctx.saved_tensors
+        da = _normalize_bwd(an, na, d_an) * g if ctx.needs_input_grad[0] else None
+        db = _normalize_bwd(bn, nb, -d_an) * g if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+def fitnet_criterion(logits, labels, feat, teacher_feat, beta=1000):
+    """criterion.py:24-36."""
+    loss_cls = cross_entropy(logits, labels)
+    loss_aux = _NormalizedMSE.apply(feat, teacher_feat)
+    return loss_cls + beta * loss_aux, loss_cls, loss_aux
+
+
+class _AttentionMSE(torch.autograd.Function):
+    """mse(normalize(||f_i||^2 over nodes), normalize(||t_i||^2 over nodes)) — at_criterion (criterion.py:44-50)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        L, st = _L(), lib.stream_ptr()
+        n = a.shape[0]
+        sa, sb = _new(n, like=a), _new(n, like=a)
+        lib.check(L.b200gnn_row_sqnorm_f32(_f32(a, "a"), n, a.shape[1], _f32(sa, "sa"), st), "row_sqnorm_f32")
+        lib.check(L.b200gnn_row_sqnorm_f32(_f32(b, "b"), n, b.shape[1], _f32(sb, "sb"), st), "row_sqnorm_f32")
+        san, na = _normalize(sa.view(1, n))
+        sbn, nb = _normalize(sb.view(1, n))
+        loss, d_san = _mse(san, sbn)
+        ctx.save_for_backward(a, b, san, na, sbn, nb, d_san)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, san, na, sbn, nb, d_san = ctx.saved_tensors
+        L, st = _L(), lib.stream_ptr()
+        out = []
+        for x, xn, nx, sign, need in ((a, san, na, 1.0, ctx.needs_input_grad[0]), (b, sbn, nb, -1.0, ctx.needs_input_grad[1])):
+            if not need:
+                out.append(None)
+                continue
+            d_s = _normalize_bwd(xn, nx, d_san * sign).view(-1)
+            d_x = torch.empty_like(x)
+            lib.check(L.b200gnn_row_sqnorm_bwd_f32(_f32(x, "x"), _f32(d_s, "d_s"), x.shape[0], x.shape[1], _f32(d_x, "d_x"), st),
+                      "row_sqnorm_bwd_f32")
+            out.append(d_x * g)
+        return tuple(out)
+
+
+def at_criterion(logits, labels, feat, teacher_feat, beta=1000):
+    """criterion.py:39-54."""
+    loss_cls = cross_entropy(logits, labels)
+    loss_aux = _AttentionMSE.apply(feat, teacher_feat)
+    return loss_cls + beta * loss_aux, loss_cls, loss_aux
+
+
+# ----------------------------------------------------------------------------------------- GSP
+class _GSP(torch.autograd.Function):
+    """mse(pairwise_k(fs), pairwise_k(ft)) over an S-row sample (criterion.py:66-86), S x S never leaves HBM twice:
+    Gram matrices by tcgen05 GEMM, similarity + MSE + d/dGram in one pass per side."""
+
+    @staticmethod
+    def forward(ctx, fs, ft, kernel: int):
+        fs, ft = fs.contiguous(), ft.contiguous()
+        L, st = _L(), lib.stream_ptr()
+        S = fs.shape[0]
+        if kernel <= 1:
+            xs, ns = _normalize(fs)
+            xt, nt = _normalize(ft)
+            sq_s = sq_t = None
+        else:
+            xs, xt, ns, nt = fs, ft, None, None
+            sq_s, sq_t = _new(S, like=fs), _new(S, like=fs)
+            lib.check(L.b200gnn_row_sqnorm_f32(_f32(xs, "xs"), S, xs.shape[1], _f32(sq_s, "sq"), st), "row_sqnorm_f32")
+            lib.check(L.b200gnn_row_sqnorm_f32(_f32(xt, "xt"), S, xt.shape[1], _f32(sq_t, "sq"), st), "row_sqnorm_f32")
+        Gs, Gt = _gemm_nt(xs, xs), _gemm_nt(xt, xt)
+        loss, part = _new(1, like=fs), _new(S, like=fs)
+        dGs, dGt = Gs.clone(), Gt.clone()
+        rc_s = _new(S, like=fs) if kernel >= 2 else None
+        rc_t = _new(S, like=fs) if kernel >= 2 else None
+        lib.check(L.b200gnn_gsp_pair_f32(_f32(dGs, "Gs"), _f32(Gt, "Gt"), _f32(sq_s, "ns"), _f32(sq_t, "nt"), S, kernel,
+                                         _f32(rc_s, "rc"), _f32(loss, "loss"), _f32(part, "part"), st), "gsp_pair_f32")
+        loss2 = _new(1, like=fs)
+        lib.check(L.b200gnn_gsp_pair_f32(_f32(dGt, "Gt"), _f32(Gs, "Gs"), _f32(sq_t, "nt"), _f32(sq_s, "ns"), S, kernel,
+                                         _f32(rc_t, "rc"), _f32(loss2, "loss"), _f32(part, "part"), st), "gsp_pair_f32")
+        ctx.kernel = kernel
+        ctx.save_for_backward(xs, xt, ns if ns is not None else xs, nt if nt is not None else xt, dGs, dGt,
+                              rc_s if rc_s is not None else xs, rc_t if rc_t is not None else xt)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, xt, ns, nt, dGs, dGt, rc_s, rc_t = ctx.saved_tensors
+        L, st = _L(), lib.stream_ptr()
+        out = []
+        for x, nrm, dG, rc, need in ((xs, ns, dGs, rc_s, ctx.needs_input_grad[0]), (xt, nt, dGt, rc_t, ctx.needs_input_grad[1])):
+            if not need:
+                out.append(None)
+                continue
+            d = _gemm_nn(dG, x)                     # dG @ x  ;  d x = 2 dG x (+ norm terms)
+            d.mul_(2.0)
+            if ctx.kernel >= 2:
+                lib.check(L.b200gnn_row_axpy_f32(_f32(x, "x"), _f32(rc, "rc"), x.shape[0], x.shape[1], 4.0, _f32(d, "d"), st),
+                          "row_axpy_f32")
+            else:
+                d = _normalize_bwd(x, nrm, d)
+            out.append(d * g)
+        return out[0], out[1], None
+
+
+def gpw_criterion(logits, labels, feat, teacher_feat, kernel='cosine', beta=1, max_samples=8192, sampled_inds=None):
+    """criterion.py:57-92."""
+    if kernel not in _KERNELS:
+        raise NotImplementedError
+    loss_cls = cross_entropy(logits, labels)
+    inds = _sample(feat.shape[0], max_samples, feat.device, sampled_inds)
+    if inds is not None:
+        feat, teacher_feat = feat[inds], teacher_feat[inds]
+    loss_aux = _GSP.apply(feat, teacher_feat, _KERNELS[kernel])
+    return loss_cls + beta * loss_aux, loss_cls, loss_aux
+
+
+# ----------------------------------------------------------------------------------------- LSP
+class LspPlan:
+    """Edge list sorted by destination (the PyG-softmax group index, criterion.py:100-104) — built once per edge_index."""
+    _cache = {}
+
+    def __init__(self, edge_index: torch.Tensor):
+        src, dst = edge_index[0], edge_index[1]
+        E = int(src.numel())
+        if E and int(max(src.max(), dst.max())) >= 2 ** 31 - 1:
+            raise lib.B200GnnError("edge_index exceeds the engine's int32 range")
+        perm = torch.argsort(dst, stable=True)
+        self.E = E
+        self.src = src[perm].to(torch.int32).contiguous()
+        self.dst = dst[perm].to(torch.int32).contiguous()
+        self.n_seg = int(dst.max()) + 1 if E else 0          # PyG softmax: N = index.max() + 1
+        counts = torch.bincount(dst, minlength=self.n_seg) if E else torch.zeros(0, dtype=torch.long, device=dst.device)
+        rowptr = torch.zeros(self.n_seg + 1, dtype=torch.long, device=dst.device)
+        torch.cumsum(counts, 0, out=rowptr[1:])
+        self.rowptr = rowptr.to(torch.int32).contiguous()
+
+    @classmethod
+    def of(cls, edge_index: torch.Tensor) -> "LspPlan":
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device))
+        plan = cls._cache.get(key)
+        if plan is None:
+            if len(cls._cache) > 8:
+                cls._cache.clear()
+            plan = cls._cache[key] = cls(edge_index)
+        return plan
+
+
+class _LSP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, teacher_feat, plan: LspPlan, kernel: int, criterion: int):
+        feat, teacher_feat = feat.contiguous(), teacher_feat.contiguous()
+        L, st = _L(), lib.stream_ptr()
+        E = plan.E
+        sim_s, sim_t, g = _new(E, like=feat), _new(E, like=feat), _new(E, like=feat)
+        for f, sim in ((feat, sim_s), (teacher_feat, sim_t)):
+            lib.check(L.b200gnn_edge_sim_f32(_f32(f, "feat"), f.shape[1], plan.src.data_ptr(), plan.dst.data_ptr(), E, kernel,
+                                             _f32(sim, "sim"), st), "edge_sim_f32")
+        loss = _new(1, like=feat)
+        part = _new(int(L.b200gnn_lsp_partials(plan.n_seg)), like=feat)
+        lib.check(L.b200gnn_lsp_segment_f32(_f32(sim_s, "sim_s"), _f32(sim_t, "sim_t"), plan.rowptr.data_ptr(), plan.n_seg, E,
+                                            criterion, _f32(g, "g"), _f32(loss, "loss"), _f32(part, "part"), st),
+                  "lsp_segment_f32")
+        ctx.plan, ctx.kernel = plan, kernel
+        ctx.save_for_backward(feat, sim_s, g)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        feat, sim_s, g = ctx.saved_tensors
+        plan = ctx.plan
+        d = torch.zeros_like(feat)
+        lib.check(_L().b200gnn_edge_sim_bwd_f32(_f32(feat, "feat"), feat.shape[1], plan.src.data_ptr(), plan.dst.data_ptr(),
+                                                plan.E, ctx.kernel, _f32(sim_s, "sim"), _f32(g, "g"), _f32(d, "d"),
+                                                lib.stream_ptr()), "edge_sim_bwd_f32")
+        return d * gout, None, None, None, None
+
+
+def lpw_criterion(logits, labels, feat, teacher_feat, edge_index, kernel='cosine', beta=100, criterion='kld'):
+    """criterion.py:95-126 (teacher features are constants of the loss, as in the reference's call sites)."""
+    if kernel not in _KERNELS or criterion not in ("kld", "mse"):
+        raise NotImplementedError
+    loss_cls = cross_entropy(logits, labels)
+    plan = LspPlan.of(edge_index)
+    loss_aux = _LSP.apply(feat, teacher_feat.detach(), plan, _KERNELS[kernel], 0 if criterion == "kld" else 1)
+    return loss_cls + beta * loss_aux, loss_cls, loss_aux
+
+
+# ----------------------------------------------------------------------------------------- G-CRD
+class _NCE(torch.autograd.Function):
+    """InfoNCE between normalised student rows and teacher rows (criterion.py:139-146): one S x S x F contraction on the
+    tensor cores, row log-sum-exp + d/dlogits in one pass, two contractions back."""
+
+    @staticmethod
+    def forward(ctx, fs, ft, nce_T: float):
+        fs, ft = fs.contiguous(), ft.contiguous()
+        L, st = _L(), lib.stream_ptr()
+        S = fs.shape[0]
+        xs, ns = _normalize(fs, 1.0 / nce_T)          # logits / T folded into the student operand
+        xt, nt = _normalize(ft)
+        Z = _gemm_nt(xs, xt)                           # [S,S]
+        loss, part = _new(1, like=fs), _new(S, like=fs)
+        lib.check(L.b200gnn_nce_rows_f32(_f32(Z, "Z"), S, _f32(loss, "loss"), _f32(part, "part"), st), "nce_rows_f32")
+        ctx.nce_T = nce_T
+        ctx.save_for_backward(xs, ns, xt, nt, Z)       # Z now holds d loss / d logits
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, ns, xt, nt, dZ = ctx.saved_tensors
+        L, st = _L(), lib.stream_ptr()
+        d_fs = d_ft = None
+        if ctx.needs_input_grad[0]:
+            d_fs = _normalize_bwd(xs, ns, _gemm_nn(dZ, xt), 1.0 / ctx.nce_T) * g
+        if ctx.needs_input_grad[1]:
+            dZt = torch.empty_like(dZ)
+            lib.check(L.b200gnn_transpose_f32(_f32(dZ, "dZ"), dZ.shape[0], dZ.shape[1], _f32(dZt, "dZt"), st), "transpose_f32")
+            d_ft = _normalize_bwd(xt, nt, _gemm_nn(dZt, xs)) * g
+        return d_fs, d_ft, None
+
+
+def nce_criterion(logits, labels, feat, teacher_feat, beta=0.5, nce_T=0.075, max_samples=8192, sampled_inds=None):
+    """criterion.py:129-149."""
+    loss_cls = cross_entropy(logits, labels)
+    inds = _sample(feat.shape[0], max_samples, feat.device, sampled_inds)
+    if inds is not None:
+        feat, teacher_feat = feat[inds], teacher_feat[inds]
+    loss_aux = _NCE.apply(feat, teacher_feat, float(nce_T))
+    return loss_cls + beta * loss_aux, loss_cls, loss_aux

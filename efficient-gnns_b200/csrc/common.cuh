@@ -81,6 +81,21 @@ __device__ __forceinline__ void vstcs(float* p, const float& v) { __stcs(p, v); 
 __device__ __forceinline__ void vstcs(float2* p, const float2& v) { __stcs(p, v); }
 __device__ __forceinline__ void vstcs(float4* p, const float4& v) { __stcs(p, v); }
 
+// out[0] = scale * sum(partial[0..n))   (one CTA, fp64, fixed order); one copy per translation unit
+static __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int n, double scale,
+                                                                  float* __restrict__ out) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += (double)partial[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(s[0] * scale);
+}
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace b200gnn

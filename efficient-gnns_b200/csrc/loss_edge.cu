@@ -1,0 +1,185 @@
+// Local Structure Preserving loss (lpw_criterion, arxiv_pyg/criterion.py:95-126) as three passes over the edge list,
+// sorted once by destination (the softmax group index, criterion.py:100-104):
+//   1. edge_sim      : per edge  k(f[src], f[dst])  for k in {cosine, cosine^2, ||.||, exp(-||.||^2/2)} — the two feature
+//                      rows are read in place (no [E,F] gathers materialised as the reference does: 4 x E x F floats);
+//   2. lsp_segment   : per destination segment, PyG softmax statistics for student and teacher, the KL (or MSE) terms,
+//                      and d loss / d sim_student for every edge;
+//   3. edge_sim_bwd  : chain rule back to the student features (atomic row adds, like the reference's index backward).
+#include "common.cuh"
+
+namespace b200gnn {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, d));
+  return v;
+}
+
+constexpr float COS_EPS = 1e-8f;   // F.cosine_similarity eps (each norm clamped separately, torch >= 1.12)
+
+// kernel ids: 0 cosine, 1 poly (cosine^2), 2 l2, 3 rbf
+__global__ void __launch_bounds__(256) edge_sim_kernel(const float* __restrict__ feat, int F, const int32_t* __restrict__ src,
+                                                       const int32_t* __restrict__ dst, int64_t E, int kernel,
+                                                       float* __restrict__ sim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t e = warp; e < E; e += nwarps) {
+    const float* a = feat + (size_t)src[e] * F;
+    const float* b = feat + (size_t)dst[e] * F;
+    float s;
+    if (kernel <= 1) {
+      float dot = 0.f, na = 0.f, nb = 0.f;
+      for (int k = lane; k < F; k += 32) { const float x = __ldg(a + k), y = __ldg(b + k); dot = fmaf(x, y, dot); na = fmaf(x, x, na); nb = fmaf(y, y, nb); }
+      dot = wsum(dot); na = wsum(na); nb = wsum(nb);
+      const float c = dot / (fmaxf(sqrtf(na), COS_EPS) * fmaxf(sqrtf(nb), COS_EPS));
+      s = kernel == 0 ? c : c * c;
+    } else {
+      float d2 = 0.f;
+      for (int k = lane; k < F; k += 32) { const float d = __ldg(a + k) - __ldg(b + k); d2 = fmaf(d, d, d2); }
+      d2 = wsum(d2);
+      s = kernel == 2 ? sqrtf(d2) : expf(-0.5f * d2);
+    }
+    if (lane == 0) sim[e] = s;
+  }
+}
+
+// One warp per destination segment [rowptr[i], rowptr[i+1]) of the dst-sorted edge arrays.
+// criterion 0: kld  loss = (1/E) sum_e xlogy(pt,pt) - pt*log(ps) ; 1: mse  loss = (1/E) sum_e (ps-pt)^2
+__global__ void __launch_bounds__(256) lsp_segment_kernel(const float* __restrict__ sim_s, const float* __restrict__ sim_t,
+                                                          const int32_t* __restrict__ rowptr, int64_t n_seg, float inv_E,
+                                                          int criterion, float* __restrict__ g, float* __restrict__ partial) {
+  __shared__ float s_acc[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < n_seg; i += (int64_t)gridDim.x * 8) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    if (b == e) continue;
+    float ms = -INFINITY, mt = -INFINITY;
+    for (int k = b + lane; k < e; k += 32) { ms = fmaxf(ms, sim_s[k]); mt = fmaxf(mt, sim_t[k]); }
+    ms = wmax(ms); mt = wmax(mt);
+    float zs = 0.f, zt = 0.f;
+    for (int k = b + lane; k < e; k += 32) { zs += expf(sim_s[k] - ms); zt += expf(sim_t[k] - mt); }
+    zs = wsum(zs) + 1e-16f; zt = wsum(zt) + 1e-16f;           // PyG softmax: e / (sum + 1e-16)
+    const float lzs = logf(zs), lzt = logf(zt);
+    if (criterion == 0) {
+      const float T = (zt - 1e-16f) / zt;                      // sum_e pt over the segment
+      for (int k = b + lane; k < e; k += 32) {
+        const float lps = (sim_s[k] - ms) - lzs, lpt = (sim_t[k] - mt) - lzt;
+        const float ps = expf(lps), pt = expf(lpt);
+        acc += pt > 0.f ? pt * (lpt - lps) : 0.f;
+        g[k] = (ps * T - pt) * inv_E;
+      }
+    } else {
+      float q = 0.f;
+      for (int k = b + lane; k < e; k += 32) {
+        const float ps = expf((sim_s[k] - ms) - lzs), pt = expf((sim_t[k] - mt) - lzt);
+        q += (ps - pt) * ps;
+      }
+      q = wsum(q);
+      for (int k = b + lane; k < e; k += 32) {
+        const float ps = expf((sim_s[k] - ms) - lzs), pt = expf((sim_t[k] - mt) - lzt);
+        const float d = ps - pt;
+        acc = fmaf(d, d, acc);
+        g[k] = 2.f * inv_E * ps * (d - q);
+      }
+    }
+  }
+  acc = wsum(acc);
+  if (lane == 0) s_acc[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_acc[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_sim_bwd_kernel(const float* __restrict__ feat, int F, const int32_t* __restrict__ src,
+                                                           const int32_t* __restrict__ dst, int64_t E, int kernel,
+                                                           const float* __restrict__ sim, const float* __restrict__ g,
+                                                           float* __restrict__ dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t e = warp; e < E; e += nwarps) {
+    const int is = src[e], id = dst[e];
+    const float* a = feat + (size_t)is * F;
+    const float* b = feat + (size_t)id * F;
+    float* da = dfeat + (size_t)is * F;
+    float* db = dfeat + (size_t)id * F;
+    float ge = g[e];
+    if (kernel <= 1) {
+      float dot = 0.f, na2 = 0.f, nb2 = 0.f;
+      for (int k = lane; k < F; k += 32) { const float x = __ldg(a + k), y = __ldg(b + k); dot = fmaf(x, y, dot); na2 = fmaf(x, x, na2); nb2 = fmaf(y, y, nb2); }
+      dot = wsum(dot); na2 = wsum(na2); nb2 = wsum(nb2);
+      const float ra = sqrtf(na2), rb = sqrtf(nb2);
+      const float na = fmaxf(ra, COS_EPS), nb = fmaxf(rb, COS_EPS);
+      const float c = dot / (na * nb);
+      if (kernel == 1) ge *= 2.f * c;
+      const float cross = ge / (na * nb);
+      const float sa = ra > COS_EPS ? ge * c / (na * na) : 0.f;   // clamped norm carries no gradient
+      const float sb = rb > COS_EPS ? ge * c / (nb * nb) : 0.f;
+      for (int k = lane; k < F; k += 32) {
+        const float x = __ldg(a + k), y = __ldg(b + k);
+        atomicAdd(da + k, cross * y - sa * x);
+        atomicAdd(db + k, cross * x - sb * y);
+      }
+    } else {
+      float coef;  // d sim / d a = coef * (a - b),  d sim / d b = -coef * (a - b)
+      if (kernel == 2) { const float d = sim[e]; coef = d > 0.f ? ge / d : 0.f; }
+      else coef = -ge * sim[e];
+      for (int k = lane; k < F; k += 32) {
+        const float v = coef * (__ldg(a + k) - __ldg(b + k));
+        atomicAdd(da + k, v);
+        atomicAdd(db + k, -v);
+      }
+    }
+  }
+}
+
+static inline int edge_grid(int64_t items) {
+  int64_t g = (items + 7) / 8;
+  if (g > 148 * 16) g = 148 * 16;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace b200gnn
+
+using namespace b200gnn;
+
+extern "C" int b200gnn_edge_sim_f32(const float* feat, int64_t F, const int32_t* src, const int32_t* dst, int64_t E,
+                                    int kernel, float* sim, void* stream) {
+  if (!feat || !sim || F <= 0 || E < 0 || kernel < 0 || kernel > 3) return B200GNN_ERR_BAD_ARG;
+  if (E == 0) return B200GNN_OK;
+  if (!src || !dst) return B200GNN_ERR_BAD_ARG;
+  edge_sim_kernel<<<edge_grid(E), 256, 0, (cudaStream_t)stream>>>(feat, (int)F, src, dst, E, kernel, sim);
+  return check_launch();
+}
+
+extern "C" int64_t b200gnn_lsp_partials(int64_t n_seg) { return edge_grid(n_seg); }
+
+extern "C" int b200gnn_lsp_segment_f32(const float* sim_s, const float* sim_t, const int32_t* rowptr, int64_t n_seg,
+                                       int64_t E, int criterion, float* g, float* loss_out, float* partial, void* stream) {
+  if (!sim_s || !sim_t || !rowptr || !g || !loss_out || !partial || n_seg <= 0 || E <= 0 || criterion < 0 || criterion > 1)
+    return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = edge_grid(n_seg);
+  int rc;
+  lsp_segment_kernel<<<grid, 256, 0, st>>>(sim_s, sim_t, rowptr, n_seg, 1.f / (float)E, criterion, g, partial);
+  if ((rc = check_launch())) return rc;
+  sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, 1.0 / (double)E, loss_out);
+  return check_launch();
+}
+
+extern "C" int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src, const int32_t* dst, int64_t E,
+                                        int kernel, const float* sim, const float* g, float* dfeat, void* stream) {
+  if (!feat || !sim || !g || !dfeat || F <= 0 || E < 0 || kernel < 0 || kernel > 3) return B200GNN_ERR_BAD_ARG;
+  if (E == 0) return B200GNN_OK;
+  if (!src || !dst) return B200GNN_ERR_BAD_ARG;
+  edge_sim_bwd_kernel<<<edge_grid(E), 256, 0, (cudaStream_t)stream>>>(feat, (int)F, src, dst, E, kernel, sim, g, dfeat);
+  return check_launch();
+}

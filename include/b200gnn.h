@@ -244,6 +244,65 @@ int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const float* G,
                                   int64_t Kin, int64_t Nout, float* workspace,
                                   void* stream);
 
+/* ------------------------------------------------------------------ *
+ * Feature-distillation criteria (arxiv_pyg/criterion.py): row / pair passes.
+ * The S x S contractions (G-CRD logits, GSP Gram matrices) run on
+ * b200gnn_gemm_tf32x3_f32; these kernels are the passes around them.
+ * ------------------------------------------------------------------ */
+/* F.normalize(x, p=2, dim=-1) * scale  (fitnet :30-31, gpw :68-69, nce :139-140); norm_out[n] = ||x|| */
+int b200gnn_row_normalize_fwd_f32(const float* x, int64_t n, int64_t F, float eps,
+                                  float scale, float* out, float* norm_out,
+                                  void* stream);
+int b200gnn_row_normalize_bwd_f32(const float* out, const float* norm,
+                                  const float* d_out, int64_t n, int64_t F,
+                                  float eps, float scale, float* d_x,
+                                  int accumulate, void* stream);
+/* scratch sizes for the deterministic scalar reductions below */
+int64_t b200gnn_reduce_slots(int64_t n);
+/* F.mse_loss(a, b): loss_out[0]; d_a (nullable) = grad_weight * 2 (a-b) / n; partial: float[b200gnn_reduce_slots(n)] */
+int b200gnn_mse_fwd_bwd_f32(const float* a, const float* b, int64_t n,
+                            float grad_weight, float* d_a, float* loss_out,
+                            float* partial, void* stream);
+/* feat.pow(2).sum(-1)  (at_criterion :44-45) and its backward */
+int b200gnn_row_sqnorm_f32(const float* x, int64_t n, int64_t F, float* out, void* stream);
+int b200gnn_row_sqnorm_bwd_f32(const float* x, const float* d_out, int64_t n,
+                               int64_t F, float* d_x, void* stream);
+/* G-CRD / InfoNCE (nce_criterion :142-146) over logits Z[S,S] (already / tau):
+ * loss_out[0] = mean_i(logsumexp_j Z_ij - Z_ii); Z is overwritten by d loss / d Z.  partial: float[S]. */
+int b200gnn_nce_rows_f32(float* Z, int64_t S, float* loss_out, float* partial, void* stream);
+int b200gnn_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
+/* GSP (gpw_criterion :66-86): Gs/Gt = Gram matrices of the sampled student/teacher rows; kernel 0 cosine,
+ * 1 poly, 2 l2, 3 rbf (ns/nt = row squared norms for 2,3).  loss_out[0] = mse(sim_s, sim_t); Gs is overwritten by
+ * d loss / d Gs; rowcoef[S] (kernels 2,3) = sum_j d loss / d ns_i.  partial: float[S]. */
+int b200gnn_gsp_pair_f32(float* Gs, const float* Gt, const float* ns, const float* nt,
+                         int64_t S, int kernel, float* rowcoef, float* loss_out,
+                         float* partial, void* stream);
+/* y[i,:] += alpha * coef[i] * x[i,:] */
+int b200gnn_row_axpy_f32(const float* x, const float* coef, int64_t n, int64_t F,
+                         float alpha, float* y, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * LSP (lpw_criterion, arxiv_pyg/criterion.py:95-126) on an edge list sorted by
+ * destination (src/dst int32[E], rowptr int32[n_seg+1] over dst).
+ * kernel: 0 cosine, 1 poly, 2 l2, 3 rbf.  criterion: 0 kld, 1 mse.
+ *   edge_sim     : sim[e] = k(feat[src[e]], feat[dst[e]])
+ *   lsp_segment  : PyG softmax per dst segment for student and teacher sims,
+ *                  loss_out[0] = the reference's loss_lpw, g[e] = d loss / d sim_s[e]
+ *   edge_sim_bwd : dfeat += chain rule of g through k (atomic row adds; dfeat pre-zeroed by the caller)
+ * ------------------------------------------------------------------ */
+int b200gnn_edge_sim_f32(const float* feat, int64_t F, const int32_t* src,
+                         const int32_t* dst, int64_t E, int kernel, float* sim,
+                         void* stream);
+int64_t b200gnn_lsp_partials(int64_t n_seg);
+int b200gnn_lsp_segment_f32(const float* sim_s, const float* sim_t,
+                            const int32_t* rowptr, int64_t n_seg, int64_t E,
+                            int criterion, float* g, float* loss_out,
+                            float* partial, void* stream);
+int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src,
+                             const int32_t* dst, int64_t E, int kernel,
+                             const float* sim, const float* g, float* dfeat,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
