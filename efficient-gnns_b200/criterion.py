@@ -93,16 +93,25 @@ def _mse(a, b, want_grad: bool = True):
     return loss, d_a
 
 
+def _pad_k(t, dim: int):
+    """Zero-pad the contraction dimension to a multiple of 4 floats (TMA needs 16-byte row pitches); exact."""
+    k = t.shape[dim]
+    if k % 4 == 0:
+        return t.contiguous()
+    pad = 4 - k % 4
+    return torch.nn.functional.pad(t, (0, pad) if dim == 1 else (0, 0, 0, pad)).contiguous()
+
+
 def _gemm_nt(a, b):
     """a[M,K] @ b[N,K]^T on the tensor cores with fp32 fidelity."""
-    hi, lo = ops.split_tf32(b.contiguous())
-    return ops.gemm_tf32x3(a.contiguous(), hi, lo)
+    hi, lo = ops.split_tf32(_pad_k(b, 1))
+    return ops.gemm_tf32x3(_pad_k(a, 1), hi, lo)
 
 
 def _gemm_nn(a, b):
     """a[M,K] @ b[K,N]."""
-    hi, lo = ops.split_tf32(b.contiguous(), transpose=True)
-    return ops.gemm_tf32x3(a.contiguous(), hi, lo)
+    hi, lo = ops.split_tf32(_pad_k(b, 0), transpose=True)
+    return ops.gemm_tf32x3(_pad_k(a, 1), hi, lo)
 
 
 def _sample(n: int, max_samples: int, device, sampled_inds=None):

@@ -1,0 +1,234 @@
+"""Host-side mirrors of the PyG layer surface the reference uses, backed by b200gnn kernels.
+
+    GCNConv(in, out, cached=)            arxiv_pyg/gnn.py:28-35, ppi_pyg/gnn.py:125
+    SAGEConv(in, out)                    arxiv_pyg/gnn.py:61-67
+    MessagePassing(aggr=).propagate      mag_pyg/gnn.py:26-68 (custom RGCNConv)
+    utils.softmax / subgraph / to_undirected
+
+Parameter names and shapes follow PyG 1.6/1.7 (``GCNConv.weight`` is [in, out], ``SAGEConv.lin_l/lin_r`` are
+``nn.Linear``), so ``state_dict``s are interchangeable with the reference's checkpoints.
+Dense contractions run on the tcgen05 3xTF32 GEMMs, aggregations on the CSR SpMM; both are differentiable.
+"""
+from __future__ import annotations
+
+import inspect
+import math
+from typing import Optional
+
+import torch
+
+from . import lib, ops
+from .engine import gcn_norm
+from .sparse import SparseTensor
+
+
+# ----------------------------------------------------------------------------------------- dense: y = x W^T (+b)
+class _LinearTC(torch.autograd.Function):
+    """x[M,in] @ weight[out,in]^T + bias on the tensor cores with fp32 fidelity; all three gradients too."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight = x.contiguous(), weight.contiguous()
+        hi, lo = ops.split_tf32(weight)                                  # B[N=out, K=in]
+        y = ops.gemm_tf32x3(x, hi, lo, bias=None if bias is None else bias.contiguous())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            hi, lo = ops.split_tf32(weight, transpose=True)              # B[N=in, K=out]
+            gx = ops.gemm_tf32x3(gy, hi, lo)
+        if ctx.needs_input_grad[1]:
+            out_f, in_f = weight.shape
+            if ops.wgrad_supported(out_f, in_f):
+                gw = ops.gemm_wgrad_tf32x3(gy, x)                        # gy^T x : [out, in]
+            else:
+                gw = torch.mm(gy.t(), x)                                 # shapes outside the tensor-core tiling
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.col_sum(gy) if gy.shape[1] % 4 == 0 and gy.shape[1] <= 1024 else gy.sum(0)
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear on the b200gnn GEMMs when the layout allows (feature widths multiples of 4), cuBLAS otherwise."""
+    if x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and x.dtype == torch.float32:
+        return _LinearTC.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+class Linear(torch.nn.Linear):
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
+
+
+def glorot(t: torch.Tensor):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+# ----------------------------------------------------------------------------------------- adjacency handling
+def _as_adj(edge_index_or_adj, num_nodes: int) -> SparseTensor:
+    """SparseTensor adj_t as is; a Tensor edge_index [2,E] (source -> target) becomes adj_t (row = target, col = source)."""
+    if isinstance(edge_index_or_adj, SparseTensor):
+        return edge_index_or_adj
+    ei = edge_index_or_adj
+    return SparseTensor(row=ei[1], col=ei[0], sparse_sizes=(num_nodes, num_nodes), is_sorted=False)
+
+
+class GCNConv(torch.nn.Module):
+    """out = D^-1/2 (A+I) D^-1/2 (x W) + b  (PyG GCNConv)."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=True, normalize=True,
+                 bias=True, **kwargs):
+        super().__init__()
+        if improved or not add_self_loops or not normalize:
+            raise NotImplementedError("the reference only uses GCNConv defaults (+cached)")
+        self.in_channels, self.out_channels, self.cached = in_channels, out_channels, cached
+        self.weight = torch.nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels)) if bias else None
+        self._cached_adj_t = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.weight)
+        if self.bias is not None:
+            torch.nn.init.zeros_(self.bias)
+        self._cached_adj_t = None
+
+    def forward(self, x, edge_index, edge_weight=None):
+        if edge_weight is not None:
+            raise NotImplementedError
+        adj = self._cached_adj_t
+        if adj is None:
+            adj = gcn_norm(_as_adj(edge_index, x.size(0)))
+            if self.cached:
+                self._cached_adj_t = adj
+        h = linear(x, self.weight.t())                 # x @ weight  (weight stored [in,out] like PyG 1.x)
+        out = ops.matmul(adj, h, "add")
+        return out if self.bias is None else out + self.bias
+
+    def __repr__(self):
+        return f"GCNConv({self.in_channels}, {self.out_channels})"
+
+
+class SAGEConv(torch.nn.Module):
+    """out = lin_l(mean_j x_j) + lin_r(x_i)  (PyG SAGEConv, Appendix A.3)."""
+
+    def __init__(self, in_channels, out_channels, normalize=False, root_weight=True, bias=True, **kwargs):
+        super().__init__()
+        if normalize or not root_weight:
+            raise NotImplementedError("the reference only uses SAGEConv defaults")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = Linear(in_channels, out_channels, bias=bias)
+        self.lin_r = Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x, edge_index):
+        adj = _as_adj(edge_index, x.size(0))
+        if adj.has_value():
+            adj = adj.set_value(None)
+        return self.lin_l(ops.matmul(adj, x, "mean")) + self.lin_r(x)
+
+    def __repr__(self):
+        return f"SAGEConv({self.in_channels}, {self.out_channels})"
+
+
+# ----------------------------------------------------------------------------------------- generic message passing
+def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = 0, dim_size: Optional[int] = None, reduce: str = "sum"):
+    """torch_scatter.scatter(src, index, dim=0, dim_size, reduce in {sum, add, mean}) as one SpMM: the [dim_size x E]
+    selection matrix has a single non-zero per column, so out = S @ src is the scatter — deterministic, no atomics."""
+    if dim != 0 or src.dim() != 2:
+        raise NotImplementedError("scatter: the reference path only reduces [E, F] messages over dim 0")
+    if reduce not in ("sum", "add", "mean"):
+        raise NotImplementedError(f"scatter reduce={reduce!r}")
+    n = int(index.max()) + 1 if dim_size is None else dim_size
+    E = index.numel()
+    sel = SparseTensor(row=index, col=torch.arange(E, device=index.device), sparse_sizes=(n, E), is_sorted=False)
+    return ops.matmul(sel, src, "mean" if reduce == "mean" else "sum")
+
+
+class MessagePassing(torch.nn.Module):
+    """The slice of PyG's MessagePassing the reference's custom RGCNConv needs (mag_pyg/gnn.py:26-68):
+    ``propagate(edge_index, x=..., **extras)`` -> ``message(x_j, **extras)`` -> scatter(aggr) onto the targets."""
+
+    def __init__(self, aggr: str = "add", flow: str = "source_to_target", node_dim: int = 0):
+        super().__init__()
+        if flow != "source_to_target" or node_dim != 0:
+            raise NotImplementedError
+        self.aggr = aggr
+
+    def propagate(self, edge_index, size=None, **kwargs):
+        x = kwargs.get("x")
+        if isinstance(edge_index, SparseTensor):
+            row, col, _ = edge_index.coo()
+            src, dst, n = col, row, edge_index.size(0)
+        else:
+            src, dst = edge_index[0], edge_index[1]
+            n = x.size(0) if x is not None else int(dst.max()) + 1
+        params = inspect.signature(self.message).parameters
+        args = {}
+        for name in params:
+            if name.endswith("_j"):
+                args[name] = kwargs[name[:-2]].index_select(0, src)
+            elif name.endswith("_i"):
+                args[name] = kwargs[name[:-2]].index_select(0, dst)
+            elif name in kwargs:
+                args[name] = kwargs[name]
+        msg = self.message(**args)
+        if dst.numel() == 0:
+            return msg.new_zeros(n, msg.shape[1])
+        return self.update(scatter(msg, dst, 0, n, self.aggr))
+
+    def message(self, x_j):
+        return x_j
+
+    def update(self, inputs):
+        return inputs
+
+
+# ----------------------------------------------------------------------------------------- utils
+def subgraph(subset, edge_index, edge_attr=None, relabel_nodes=False, num_nodes=None):
+    """torch_geometric.utils.subgraph: induced subgraph, edge order preserved, ids = positions in subset."""
+    n = num_nodes if num_nodes is not None else int(edge_index.max()) + 1
+    if subset.dtype == torch.bool:
+        n_mask = subset
+        subset = subset.nonzero().view(-1)
+    else:
+        n = max(n, int(subset.max()) + 1) if subset.numel() else n
+        n_mask = torch.zeros(n, dtype=torch.bool, device=edge_index.device)
+        n_mask[subset] = True
+    mask = n_mask[edge_index[0]] & n_mask[edge_index[1]]
+    ei = edge_index[:, mask]
+    if relabel_nodes:
+        n_idx = torch.zeros(n_mask.numel(), dtype=torch.long, device=edge_index.device)
+        n_idx[subset] = torch.arange(subset.numel(), device=edge_index.device)
+        ei = n_idx[ei]
+    return ei, (edge_attr[mask] if edge_attr is not None else None)
+
+
+def to_undirected(edge_index, num_nodes=None):
+    n = num_nodes if num_nodes is not None else int(edge_index.max()) + 1
+    r, c, _ = SparseTensor(row=edge_index[0], col=edge_index[1], sparse_sizes=(n, n)).to_symmetric().coo()
+    return torch.stack([r, c])
+
+
+def softmax(src, index, ptr=None, num_nodes=None):
+    """torch_geometric.utils.softmax(src, index): e / (sum_e + 1e-16) with the max subtracted per group.
+    Composed from differentiable torch scatter primitives on the device (index plumbing); the LSP criterion in
+    efficient_gnns_b200.criterion fuses this with the similarity and the KL terms instead."""
+    n = int(index.max()) + 1 if num_nodes is None else num_nodes
+    shape = (n,) + tuple(src.shape[1:])
+    idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    m = torch.full(shape, float("-inf"), dtype=src.dtype, device=src.device).scatter_reduce_(0, idx, src.detach(), "amax")
+    e = (src - m.index_select(0, index)).exp()
+    s = torch.zeros(shape, dtype=src.dtype, device=src.device).scatter_add_(0, idx, e)
+    return e / (s.index_select(0, index) + 1e-16)

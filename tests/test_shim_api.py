@@ -1,0 +1,67 @@
+"""The shim packages expose every name the reference imports, importable without a GPU."""
+import importlib
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+SHIM = ROOT / "efficient-gnns_b200" / "shim"
+
+
+@pytest.fixture()
+def shim_path():
+    sys.path.insert(0, str(SHIM))
+    yield
+    sys.path.remove(str(SHIM))
+    for m in [m for m in sys.modules if m.split(".")[0] in ("torch_geometric", "torch_sparse", "torch_scatter", "ogb")]:
+        del sys.modules[m]
+
+
+def test_reference_import_surface(shim_path):
+    import torch_geometric
+    import torch_geometric.transforms as T
+    from torch_geometric.nn import GCNConv, SAGEConv, MessagePassing
+    from torch_geometric.utils import softmax, to_dense_adj, subgraph, negative_sampling, add_self_loops, to_undirected
+    from torch_geometric.utils.hetero import group_hetero_graph
+    from torch_geometric.data import Data, GraphSAINTRandomWalkSampler, DataLoader
+    from torch_geometric.datasets import PPI
+    from torch_sparse import SparseTensor
+    from torch_scatter import scatter
+    from ogb.nodeproppred import PygNodePropPredDataset, Evaluator
+    assert callable(T.ToSparseTensor) and torch_geometric.__version__
+
+
+def test_dataset_stub_and_transform_on_cpu(shim_path):
+    import torch_geometric.transforms as T
+    from ogb.nodeproppred import PygNodePropPredDataset, Evaluator
+    ds = PygNodePropPredDataset(name="ogbn-arxiv-plumbing", transform=T.ToSparseTensor())
+    data = ds[0]
+    assert data.edge_index is None and data.adj_t.nnz() == 50_000
+    data.adj_t = data.adj_t.to_symmetric()
+    row, col, _ = data.adj_t.coo()
+    assert bool((row[1:] >= row[:-1]).all())
+    split = ds.get_idx_split()
+    assert set(split) == {"train", "valid", "test"} and ds.num_classes == 40
+    acc = Evaluator("ogbn-arxiv").eval({"y_true": data.y[split["train"]], "y_pred": data.y[split["train"]]})["acc"]
+    assert acc == 1.0
+
+
+def test_subgraph_and_hetero_match_oracle(shim_path):
+    import numpy as np
+    from torch_geometric.utils import subgraph, to_undirected
+    from torch_geometric.utils.hetero import group_hetero_graph
+    from oracle import graph as og
+    g = torch.Generator().manual_seed(0)
+    ei = torch.randint(0, 50, (2, 400), generator=g)
+    subset = torch.randperm(50, generator=g)[:20]
+    got, _ = subgraph(subset, ei, relabel_nodes=True)
+    ref, _ = og.subgraph(subset.numpy(), ei.numpy(), True)
+    assert np.array_equal(got.numpy(), ref)
+    und = to_undirected(ei[:, ei[0] != ei[1]], 50)
+    assert np.array_equal(und.numpy(), og.to_undirected(ei[:, ei[0] != ei[1]].numpy(), 50))
+    eid = {("a", "r", "b"): torch.tensor([[0, 1], [2, 0]]), ("b", "s", "a"): torch.tensor([[1], [1]])}
+    e, et, nt, li, k2i = group_hetero_graph(eid, {"a": 2, "b": 3})
+    assert e.tolist() == [[0, 1, 3], [4, 2, 1]] and et.tolist() == [0, 0, 1] and nt.tolist() == [0, 0, 1, 1, 1]
+    assert li.tolist() == [0, 1, 0, 1, 2] and k2i["b"] == 1
