@@ -188,27 +188,44 @@ def run_single(args):
     clocks = clk.summary()
     losses = tr.loss_out.tolist()
 
-    # ---- phase 2: end to end — every step copies its inputs from pinned host memory and reads the losses back
+    # ---- phase 2: end to end — every step copies ITS inputs from pinned host memory and its losses are read back.
+    # Two device input sets + two captured graphs: the upload of step k+1 (copy stream) overlaps the compute of step k.
     h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2 = {k: torch.empty_like(v) for k, v in d.items()}
+    for k in d2:
+        d2[k].copy_(d[k])
+    tr.capture(d2["x"], d2["y"], d2["idx"], d2["t"], warmup=1, key=1)
+    sets = [d, d2]
     loss_host = torch.empty(3).pin_memory()
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
+    uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
+    def upload(i):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_stream(main)          # previous step done with the static buffers
-            for k in d:
-                d[k].copy_(host[k], non_blocking=True)
-        main.wait_stream(copy_stream)
-        tr.replay()
-        loss_host.copy_(tr.loss_out, non_blocking=True)
+            copy_stream.wait_event(consumed[i])          # the step that last read this set has finished
+            for k in sets[i]:
+                sets[i][k].copy_(host[k], non_blocking=True)
+            uploaded[i].record(copy_stream)
 
-    for _ in range(max(3, args.warmup // 2)):
-        e2e_step()
+    def e2e_loop(n_steps):
+        for i in (0, 1):
+            consumed[i].record(main)
+        upload(0)
+        for step in range(n_steps):
+            i = step & 1
+            if step + 1 < n_steps:
+                upload(1 - i)
+            main.wait_event(uploaded[i])
+            tr.replay(i)
+            consumed[i].record(main)
+            loss_host.copy_(tr.loss_out, non_blocking=True)
+
+    e2e_loop(max(3, args.warmup // 2))
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1) / args.steps
@@ -264,7 +281,9 @@ def run_single(args):
                          "launches_timed": len(evs), "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": 6 * nnz / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "note": "features, labels, teacher logits and train index re-uploaded from pinned host memory every "
+                            "step (double-buffered, overlapping the previous step), 3 loss scalars read back"},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
             "clocks": clocks, "loss": losses}
     print(json.dumps(line), flush=True)

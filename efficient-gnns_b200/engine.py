@@ -299,8 +299,10 @@ class GCNStudentTrainer:
         return self.loss_out
 
     # ------------------------------------------------------------------ CUDA graph
-    def capture(self, x, y, train_idx, teacher_logits=None, warmup: int = 2):
-        """Capture the step on static input buffers; afterwards ``replay()`` runs one full step."""
+    def capture(self, x, y, train_idx, teacher_logits=None, warmup: int = 2, key: int = 0):
+        """Capture the step on static input buffers; afterwards ``replay(key)`` runs one full step.
+        Several input-buffer sets can be captured (key = 0, 1, ...) so that uploads of the next step's inputs overlap
+        the current step (activations and parameters are shared between the graphs)."""
         self._static.update(x=x, y=y, train_idx=train_idx, teacher=teacher_logits)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -309,13 +311,16 @@ class GCNStudentTrainer:
                 self._step_impl(x, y, train_idx, teacher_logits)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        if self._graph is None:
+            self._graph = {}
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             self._step_impl(x, y, train_idx, teacher_logits)
+        self._graph[key] = g
         return self
 
-    def replay(self) -> torch.Tensor:
-        self._graph.replay()
+    def replay(self, key: int = 0) -> torch.Tensor:
+        self._graph[key].replay()
         return self.loss_out
 
     # ------------------------------------------------------------------ accounting

@@ -35,11 +35,55 @@ def spmm_scatter(row, col, val: Optional[torch.Tensor], x, n_rows: int, reduce: 
     return scatter(msg, row, n_rows, reduce)
 
 
+class _CsrMatmul(torch.autograd.Function):
+    """A @ x with the backward restated the way upstream torch_sparse does it: dX = A^T @ dY through a
+    PRE-BUILT CSR of A^T (the cached colptr / csr2csc view), instead of autograd re-deriving a transpose per call."""
+
+    @staticmethod
+    def forward(ctx, x, A, At):
+        ctx.At = At
+        return A @ x
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.At @ g.contiguous(), None, None
+
+
+_CSR_CACHE = {}
+
+
+def _csr_pair(rowptr, col, v, n_rows, n_cols):
+    """(A, A^T) as torch sparse CSR tensors, cached per (rowptr, col, val) identity like upstream's SparseStorage."""
+    key = (rowptr.data_ptr(), col.data_ptr(), v.data_ptr(), v.dtype, n_rows, n_cols)
+    hit = _CSR_CACHE.get(key)
+    if hit is None:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A = torch.sparse_csr_tensor(rowptr, col, v, size=(n_rows, n_cols))
+            row = torch.repeat_interleave(torch.arange(n_rows), rowptr[1:] - rowptr[:-1])
+            perm = torch.argsort(col * n_rows + row, stable=True)
+            ct = torch.zeros(n_cols + 1, dtype=torch.long)
+            torch.cumsum(torch.bincount(col, minlength=n_cols), 0, out=ct[1:])
+            At = torch.sparse_csr_tensor(ct, row[perm], v[perm], size=(n_cols, n_rows))
+        if len(_CSR_CACHE) > 16:
+            _CSR_CACHE.clear()
+        hit = _CSR_CACHE[key] = (A, At, rowptr, col, v)     # keep the keyed tensors alive
+    return hit[0], hit[1]
+
+
 def spmm_csr(rowptr, col, val: Optional[torch.Tensor], x, n_rows: int, reduce: str = "sum"):
     """Form (ii): torch.sparse_csr_tensor @ x (MKL); mean divides by max(rowcount,1)."""
     v = torch.ones(col.numel(), dtype=x.dtype) if val is None else val.to(x.dtype)
-    A = torch.sparse_csr_tensor(rowptr, col, v, size=(n_rows, x.shape[0]))
-    out = A @ x
+    if val is not None and v.data_ptr() != val.data_ptr():
+        A = torch.sparse_csr_tensor(rowptr, col, v, size=(n_rows, x.shape[0]))
+        out = A @ x
+    elif val is None:
+        A = torch.sparse_csr_tensor(rowptr, col, v, size=(n_rows, x.shape[0]))
+        out = A @ x
+    else:
+        A, At = _csr_pair(rowptr, col, v, n_rows, x.shape[0])
+        out = _CsrMatmul.apply(x, A, At)
     if reduce == "mean":
         cnt = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(x.dtype)
         out = out / cnt.view(-1, 1)
