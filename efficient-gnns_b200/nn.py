@@ -232,3 +232,161 @@ def softmax(src, index, ptr=None, num_nodes=None):
     e = (src - m.index_select(0, index)).exp()
     s = torch.zeros(shape, dtype=src.dtype, device=src.device).scatter_add_(0, idx, e)
     return e / (s.index_select(0, index) + 1e-16)
+
+
+# ----------------------------------------------------------------------------------------- graph attention
+class _GatAggregate(torch.autograd.Function):
+    """out[i,h,:] = sum_{j->i} softmax_j(leaky_relu(el[j,h] + er[i,h])) * ft[j,h,:]   (DGL apply_edges + edge_softmax +
+    update_all, arxiv_dgl/models.py:202-217; PyG GATConv's message/aggregate) with its hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, ft, el, er, adj: SparseTensor, H: int, D: int, slope: float, eps: float):
+        ft, el = ft.contiguous(), el.contiguous()
+        er = None if er is None else er.contiguous()
+        st = adj.storage
+        G = st.engine_csr_unweighted() if st.value() is None else st.engine_csr()
+        L, s = lib.load(), lib.stream_ptr()
+        n = G.n_rows
+        a = torch.empty(G.nnz, H, dtype=torch.float32, device=ft.device)
+        lib.check(L.b200gnn_gat_edge_softmax_f32(G.rowptr.data_ptr(), G.col.data_ptr(), el.data_ptr(),
+                                                 None if er is None else er.data_ptr(), n, H, slope, eps, a.data_ptr(), s),
+                  "gat_edge_softmax_f32")
+        out = torch.empty(n, H * D, dtype=torch.float32, device=ft.device)
+        _gat_aggregate(G, None, a, ft, out, H, D)
+        ctx.adj, ctx.dims, ctx.slope = adj, (H, D), slope
+        ctx.save_for_backward(ft, el, er if er is not None else el, a)
+        ctx.has_er = er is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ft, el, er, a = ctx.saved_tensors
+        H, D = ctx.dims
+        er = er if ctx.has_er else None
+        dout = dout.contiguous()
+        st = ctx.adj.storage
+        G = st.engine_csr_unweighted() if st.value() is None else st.engine_csr()
+        L, s = lib.load(), lib.stream_ptr()
+        dpre = torch.empty_like(a)
+        der = torch.empty(G.n_rows, H, dtype=torch.float32, device=ft.device) if er is not None else None
+        lib.check(L.b200gnn_gat_bwd_rows_f32(G.rowptr.data_ptr(), G.col.data_ptr(), a.data_ptr(), ft.data_ptr(), ft.stride(0),
+                                             dout.data_ptr(), dout.stride(0), el.data_ptr(),
+                                             None if er is None else er.data_ptr(), G.n_rows, H, D, ctx.slope, dpre.data_ptr(),
+                                             None if der is None else der.data_ptr(), s), "gat_bwd_rows_f32")
+        Gt = st.engine_csc("value")                              # transposed graph as CSR (rows = sources)
+        perm = _csr2csc_i32(st)
+        dft = torch.empty(Gt.n_rows, H * D, dtype=torch.float32, device=ft.device)
+        _gat_aggregate(Gt, perm, a, dout, dft, H, D)
+        d_el = torch.empty(Gt.n_rows, H, dtype=torch.float32, device=ft.device)
+        lib.check(L.b200gnn_segment_sum_heads_f32(Gt.rowptr.data_ptr(), perm.data_ptr(), dpre.data_ptr(), Gt.n_rows, H,
+                                                  d_el.data_ptr(), s), "segment_sum_heads_f32")
+        return dft, d_el, der, None, None, None, None, None
+
+
+def _csr2csc_i32(st) -> torch.Tensor:
+    p = st._engine.get("csr2csc_i32")
+    if p is None:
+        p = st._engine["csr2csc_i32"] = st.csr2csc().to(torch.int32).contiguous()
+    return p
+
+
+def _gat_aggregate(G, eidx, a, ft, out, H, D):
+    lib.check(lib.load().b200gnn_gat_aggregate_f32(
+        G.rowptr.data_ptr(), G.col.data_ptr(), None if eidx is None else eidx.data_ptr(), a.data_ptr(), ft.data_ptr(),
+        ft.stride(0), out.data_ptr(), out.stride(0), G.n_rows, H, D, G.chunk_rowptr.data_ptr(), G.n_chunks, G.hub_threshold,
+        G.hub_rows.data_ptr() if G.n_hub else None, G.n_hub, lib.stream_ptr()), "gat_aggregate_f32")
+
+
+def gat_aggregate(ft, el, er, adj: SparseTensor, heads: int, negative_slope: float = 0.2, softmax_eps: float = 0.0):
+    """ft [N, heads*D], el [N, heads], er [N_dst, heads] or None, adj rows = destinations -> [N_dst, heads*D]."""
+    return _GatAggregate.apply(ft, el, er, adj, heads, ft.shape[1] // heads, float(negative_slope), float(softmax_eps))
+
+
+class DGLGATConv(torch.nn.Module):
+    """The reference's DGL GATConv (arxiv_dgl/models.py:95-236) on a SparseTensor adjacency (rows = destinations):
+    same parameters (fc, attn_l, attn_r, res_fc), symmetric degree normalisation, optional residual / activation.
+    Stochastic edge/attention dropout of the teacher's training loop is not part of the distillation hot path."""
+
+    def __init__(self, in_feats, out_feats, num_heads=1, feat_drop=0.0, attn_drop=0.0, edge_drop=0.0, negative_slope=0.2,
+                 use_attn_dst=True, residual=False, activation=None, allow_zero_in_degree=False, use_symmetric_norm=False):
+        super().__init__()
+        if attn_drop > 0 or edge_drop > 0:
+            raise NotImplementedError("attention / edge dropout (teacher training only) is not implemented")
+        self._num_heads, self._out_feats, self._slope = num_heads, out_feats, negative_slope
+        self._use_symmetric_norm, self._activation = use_symmetric_norm, activation
+        self.fc = Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = torch.nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = torch.nn.Parameter(torch.empty(1, num_heads, out_feats)) if use_attn_dst else None
+        self.feat_drop = torch.nn.Dropout(feat_drop)
+        self.res_fc = Linear(in_feats, num_heads * out_feats, bias=False) if residual else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = torch.nn.init.calculate_gain("relu")
+        torch.nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        torch.nn.init.xavier_normal_(self.attn_l, gain=gain)
+        if self.attn_r is not None:
+            torch.nn.init.xavier_normal_(self.attn_r, gain=gain)
+        if self.res_fc is not None:
+            torch.nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+
+    def forward(self, adj_t: SparseTensor, feat):
+        H, D = self._num_heads, self._out_feats
+        h = self.feat_drop(feat)
+        ft = self.fc(h).view(-1, H, D)
+        st = adj_t.storage
+        if self._use_symmetric_norm:
+            out_deg = torch.bincount(st.col(), minlength=adj_t.size(1)).float().clamp(min=1)
+            ft = ft * out_deg.pow(-0.5).view(-1, 1, 1)
+        el = (ft * self.attn_l).sum(-1)
+        er = (ft * self.attn_r).sum(-1) if self.attn_r is not None else None
+        rst = gat_aggregate(ft.reshape(-1, H * D), el, er, adj_t, H, self._slope, 0.0).view(-1, H, D)
+        if self._use_symmetric_norm:
+            rst = rst * st.rowcount().float().clamp(min=1).pow(0.5).view(-1, 1, 1)
+        if self.res_fc is not None:
+            rst = rst + self.res_fc(h).view(h.shape[0], -1, D)
+        return self._activation(rst) if self._activation is not None else rst
+
+
+class GATConv(torch.nn.Module):
+    """PyG 1.6/1.7 GATConv as used by ppi_pyg/gnn.py:27-31,53-61: shared ``lin`` (no bias), att_l / att_r, self-loops
+    re-added, PyG softmax (eps 1e-16), concat or head-mean, bias."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 bias=True, **kwargs):
+        super().__init__()
+        if dropout > 0:
+            raise NotImplementedError("attention dropout is not implemented")
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
+        self.lin_l = Linear(in_channels, heads * out_channels, bias=False)
+        self.lin_r = self.lin_l
+        self.att_l = torch.nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_r = torch.nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(heads * out_channels if concat else out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.lin_l.weight); glorot(self.att_l); glorot(self.att_r)
+        if self.bias is not None:
+            torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index):
+        H, C = self.heads, self.out_channels
+        n = x.size(0)
+        adj = _as_adj(edge_index, n)
+        if self.add_self_loops:
+            adj = adj.set_value(None).fill_diag(1.0) if adj.has_value() else _fill_diag_pattern(adj)
+        xl = self.lin_l(x).view(-1, H, C)
+        al, ar = (xl * self.att_l).sum(-1), (xl * self.att_r).sum(-1)
+        out = gat_aggregate(xl.reshape(-1, H * C), al, ar, adj, H, self.negative_slope, 1e-16).view(-1, H, C)
+        out = out.reshape(-1, H * C) if self.concat else out.mean(dim=1)
+        return out if self.bias is None else out + self.bias
+
+
+def _fill_diag_pattern(adj: SparseTensor) -> SparseTensor:
+    """remove_self_loops + add_self_loops on a value-less adjacency."""
+    row, col, _ = adj.coo()
+    off = row != col
+    d = torch.arange(min(adj.sparse_sizes()), device=row.device)
+    return SparseTensor(row=torch.cat([row[off], d]), col=torch.cat([col[off], d]), sparse_sizes=adj.sparse_sizes(), is_sorted=False)

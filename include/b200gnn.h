@@ -303,6 +303,38 @@ int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src,
                              const float* sim, const float* g, float* dfeat,
                              void* stream);
 
+/* ------------------------------------------------------------------ *
+ * Graph attention (BASELINE config 4): per-destination edge softmax and
+ * multi-head weighted aggregation, CSR rows = destinations, col = sources.
+ *   DGL GATConv.forward   arxiv_dgl/models.py:196-217  (softmax_eps = 0)
+ *   PyG GATConv           ppi_pyg/gnn.py:27-31          (softmax_eps = 1e-16)
+ *   gat_edge_softmax : a[e,h] = softmax_e( leaky_relu(el[col[e],h] + er[row,h]) )   er NULL => el only
+ *   gat_aggregate    : out[r, h*D+d] = sum_e a[eidx ? eidx[e] : e, h] * ft[col[e], h*D+d]
+ *                      (forward on the CSR; d ft on the transposed CSR with eidx = csr2csc)
+ *   gat_bwd_rows     : given d out, writes dpre[e,h] = d loss / d (el+er)[e,h] and der[r,h]
+ *   segment_sum_heads: out[r,h] = sum_e vals[eidx[e],h]  (d el over the transposed CSR)
+ * H <= 16.  chunk_rowptr / hub_rows: the plans of b200gnn_csr_chunk_plan / b200gnn_csr_hub_fill.
+ * ------------------------------------------------------------------ */
+int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t* col,
+                                 const float* el, const float* er, int64_t n_rows,
+                                 int64_t H, float negative_slope, float softmax_eps,
+                                 float* a, void* stream);
+int b200gnn_gat_aggregate_f32(const int32_t* rowptr, const int32_t* col,
+                              const int32_t* eidx, const float* a, const float* ft,
+                              int64_t ldf, float* out, int64_t ldo, int64_t n_rows,
+                              int64_t H, int64_t D, const int32_t* chunk_rowptr,
+                              int64_t n_chunks, int32_t hub_threshold,
+                              const int32_t* hub_rows, int64_t n_hub, void* stream);
+int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const float* a,
+                             const float* ft, int64_t ldf, const float* dout,
+                             int64_t ldd, const float* el, const float* er,
+                             int64_t n_rows, int64_t H, int64_t D,
+                             float negative_slope, float* dpre, float* der,
+                             void* stream);
+int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx,
+                                  const float* vals, int64_t n_rows, int64_t H,
+                                  float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

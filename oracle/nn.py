@@ -72,3 +72,21 @@ def sage_forward(x, rowptr, col, params: List[dict], bn_gamma, bn_beta, dropout_
         hidden = x
     q = params[-1]
     return sage_conv(x, rowptr, col, q["w_l"], q["b_l"], q["w_r"]), hidden
+
+
+def gat_aggregate(ft, el, er, row, col, n_dst: int, heads: int, negative_slope: float = 0.2, softmax_eps: float = 0.0):
+    """Edge attention + weighted aggregation restated with plain torch (DGL: apply_edges(u_add_v) -> leaky_relu ->
+    edge_softmax -> update_all(u_mul_e, sum), arxiv_dgl/models.py:202-217; PyG GATConv with softmax_eps=1e-16).
+    row = destination, col = source of every edge; ft [N, H*D], el [N, H], er [n_dst, H] or None."""
+    H = heads
+    D = ft.shape[1] // H
+    e = el.index_select(0, col) + (er.index_select(0, row) if er is not None else 0)
+    e = torch.where(e > 0, e, e * negative_slope)
+    idx = row.view(-1, 1).expand_as(e)
+    m = torch.full((n_dst, H), float("-inf"), dtype=e.dtype).scatter_reduce_(0, idx, e.detach(), "amax", include_self=True)
+    ex = (e - m.index_select(0, row)).exp()
+    s = torch.zeros(n_dst, H, dtype=e.dtype).scatter_add_(0, idx, ex)
+    a = ex / (s.index_select(0, row) + softmax_eps)
+    msg = ft.index_select(0, col).view(-1, H, D) * a.unsqueeze(-1)
+    out = torch.zeros(n_dst, H, D, dtype=ft.dtype).index_add_(0, row, msg)
+    return out.reshape(n_dst, H * D)

@@ -1,0 +1,89 @@
+"""Graph-attention kernels (edge softmax + multi-head aggregation, forward and backward) vs the fp64 oracle; the DGL-style
+and PyG-style modules on top of them."""
+import numpy as np
+import pytest
+import torch
+
+import efficient_gnns_b200  # noqa: F401
+from conftest import rel_err
+from efficient_gnns_b200 import nn as bnn
+from efficient_gnns_b200.sparse import SparseTensor
+from efficient_gnns_b200.synthetic import skewed_edges
+from oracle import graph as og, nn as onn
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def graph(n, e, seed, self_loops=True):
+    ei = skewed_edges(n, e, seed).numpy()
+    row, col, _ = og.to_sparse_adj_t(ei, n)
+    r, c = og.to_symmetric(row, col, n)
+    if self_loops:
+        r, c, _ = og.fill_diag(r, c, np.ones(r.shape[0], dtype=np.float32), n)
+    return torch.from_numpy(r), torch.from_numpy(c)
+
+
+@pytest.mark.parametrize("H,D,with_er,eps", [(8, 32, True, 0.0), (3, 250, False, 0.0), (4, 16, True, 1e-16), (1, 7, True, 0.0),
+                                             (6, 10, True, 0.0)])
+def test_gat_aggregate_forward_backward(H, D, with_er, eps):
+    n = 4000
+    r, c = graph(n, 30_000, H + D)          # skewed: contains hub rows above the split threshold
+    g = torch.Generator().manual_seed(D)
+    ft = torch.randn(n, H * D, generator=g)
+    el, er = torch.randn(n, H, generator=g), (torch.randn(n, H, generator=g) if with_er else None)
+    w = torch.randn(n, H * D, generator=g)
+    ftr, elr = ft.double().requires_grad_(True), el.double().requires_grad_(True)
+    err = er.double().requires_grad_(True) if with_er else None
+    ref = onn.gat_aggregate(ftr, elr, err, r, c, n, H, 0.2, eps)
+    (ref * w.double()).sum().backward()
+    adj = SparseTensor(row=r.cuda(), col=c.cuda(), sparse_sizes=(n, n), is_sorted=True)
+    assert adj.storage.engine_csr_unweighted().n_hub > 0
+    ftc, elc = ft.cuda().requires_grad_(True), el.cuda().requires_grad_(True)
+    erc = er.cuda().requires_grad_(True) if with_er else None
+    out = bnn.gat_aggregate(ftc, elc, erc, adj, H, 0.2, eps)
+    (out * w.cuda()).sum().backward()
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(ftc.grad, ftr.grad) < 2e-5
+    assert rel_err(elc.grad, elr.grad) < 2e-5
+    if with_er:
+        assert rel_err(erc.grad, err.grad) < 2e-5
+    out2 = bnn.gat_aggregate(ftc, elc, erc, adj, H, 0.2, eps)
+    assert torch.equal(out, out2)
+
+
+def test_dgl_style_gatconv_layer_matches_oracle_composition():
+    n, Fin, H, D = 1500, 64, 3, 20
+    r, c = graph(n, 9000, 1)
+    adj = SparseTensor(row=r.cuda(), col=c.cuda(), sparse_sizes=(n, n), is_sorted=True)
+    torch.manual_seed(0)
+    layer = bnn.DGLGATConv(Fin, D, num_heads=H, residual=True, use_symmetric_norm=True, activation=None).cuda()
+    x = torch.randn(n, Fin)
+    out = layer(adj, x.cuda())
+    # oracle composition of arxiv_dgl/models.py:171-230 in fp64
+    W, al, ar, Wr = (p.detach().cpu().double() for p in (layer.fc.weight, layer.attn_l, layer.attn_r, layer.res_fc.weight))
+    xd = x.double()
+    ft = (xd @ W.t()).view(n, H, D)
+    out_deg = torch.bincount(c, minlength=n).double().clamp(min=1)
+    ft = ft * out_deg.pow(-0.5).view(-1, 1, 1)
+    el, er = (ft * al).sum(-1), (ft * ar).sum(-1)
+    rst = onn.gat_aggregate(ft.reshape(n, H * D), el, er, r, c, n, H, 0.2, 0.0).view(n, H, D)
+    in_deg = torch.bincount(r, minlength=n).double().clamp(min=1)
+    rst = rst * in_deg.pow(0.5).view(-1, 1, 1) + (xd @ Wr.t()).view(n, H, D)
+    assert rel_err(out, rst) < 1e-5
+
+
+def test_pyg_style_gatconv_adds_self_loops_and_concats():
+    n, Fin, H, C = 800, 48, 4, 12
+    ei = skewed_edges(n, 5000, 2)
+    torch.manual_seed(1)
+    layer = bnn.GATConv(Fin, C, heads=H).cuda()
+    x = torch.randn(n, Fin)
+    out = layer(x.cuda(), ei.cuda())
+    assert out.shape == (n, H * C)
+    W, al, ar, b = (p.detach().cpu().double() for p in (layer.lin_l.weight, layer.att_l, layer.att_r, layer.bias))
+    xl = (x.double() @ W.t()).view(n, H, C)
+    src, dst = ei[0], ei[1]
+    loops = torch.arange(n)
+    row, col = torch.cat([dst, loops]), torch.cat([src, loops])
+    ref = onn.gat_aggregate(xl.reshape(n, H * C), (xl * al).sum(-1), (xl * ar).sum(-1), row, col, n, H, 0.2, 1e-16) + b
+    assert rel_err(out, ref) < 1e-5
