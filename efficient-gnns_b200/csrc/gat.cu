@@ -12,7 +12,7 @@
 
 namespace b200gnn {
 
-constexpr int GAT_THREADS = 256, GAT_WARPS = 8, GAT_MAXH = 16, GAT_MAXJ = 8;
+constexpr int GAT_THREADS = 256, GAT_WARPS = 8, GAT_MAXH = 16, GAT_MAXJ = 12;
 
 __device__ __forceinline__ float gsum(float v) {
 #pragma unroll
