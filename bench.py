@@ -12,6 +12,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ["NCCL_DEBUG"] = "WARN"   # before torch/NCCL load: keep NCCL's version banner off stdout (ONE JSON line)
 import subprocess
 import sys
 import threading

@@ -168,3 +168,22 @@ def test_sharded_trainer_world1_matches_plain_engine():
     for l in range(tr.L):
         assert ((sh.gW[l] - tr.gW[l]).norm() / tr.gW[l].norm()).item() < 2e-3
     assert sh.exchange_bytes_per_step() == 0
+
+
+def test_config0_plumbing_shape_two_layer_gcn():
+    """BASELINE.json configs[0]: 2-layer GCN, synthetic 10k-node / 50k-edge graph, 64-d — the reference's CPU-runnable
+    case, here as a parity case of the CUDA engine against the oracle (supervised step, dropout injected)."""
+    from efficient_gnns_b200.synthetic import PLUMBING, make_node_dataset
+    ds = make_node_dataset(PLUMBING, seed=0)
+    n = ds.num_nodes
+    row, col, _ = og.to_sparse_adj_t(ds.edge_index.numpy(), n)
+    r, c = og.to_symmetric(row, col, n)
+    adj = SparseTensor(row=torch.from_numpy(r).cuda(), col=torch.from_numpy(c).cuda(), sparse_sizes=(n, n), is_sorted=True)
+    tr = GCNStudentTrainer(adj, [64, 64, 40], dropout=0.5, lr=0.01, seed=0)
+    masks = [ops.dropout_mask(n, 64, 0.5, tr.seed, tr.dropout_offset(0, 0)).cpu().bool()]
+    x, y, idx = ds.x, ds.y.squeeze(1), ds.split_idx["train"]
+    ref_logits, ref_hidden, ref_loss, ref_grads, _ = oracle_step(tr, (r, c), x, y, ds.teacher_logits, idx, masks, kd=False)
+    loss = tr.train_step(x.cuda(), y.cuda(), idx.cuda(), None).cpu()
+    assert rel_err(tr.Y[-1], ref_logits) < 1e-5 and rel_err(tr.A[-1], ref_hidden) < 1e-5
+    assert abs(loss[0] - ref_loss[0]) < 1e-5 * abs(ref_loss[0])
+    assert rel_err(tr.gW[1], ref_grads[4]) < 2e-5 and rel_err(tr.gW[0], ref_grads[0]) < 5e-5
