@@ -41,7 +41,7 @@ struct SpmmParams {
   int64_t ldx, ldy;  // in floats
   int32_t n_rows, K, nvec;
   int32_t hub_threshold, seg_len, n_hub, n_seg, n_chunks;
-  int32_t mean, stream_store, main_grid;
+  int32_t mean, stream_store, main_grid, l2_hint;
 };
 
 struct LaneMap {
@@ -293,6 +293,18 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
+// The gathered operand is the only stream with reuse (every row of X is read ~deg times): ask L2 to keep it
+// (evict_last) while col/val/Y stream through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -313,6 +325,8 @@ __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const i
   const int chunk = cta * SPMM_WARPS + warp;
   const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
   const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
+  const uint64_t pol = l2_policy_evict_last();
+  const bool hint = p.l2_hint != 0;
 
   auto flush = [&](int row, int deg, float4 (&acc)[CH]) {
 #pragma unroll
@@ -383,7 +397,9 @@ __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const i
         const float4* src = Xv + (size_t)cc * ldxv + lane;
         float4* dst = ring + (jj % D) * (CH * 32) + lane;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) cp_async16(dst + 32 * j, src + 32 * j);
+        for (int j = 0; j < CH; ++j) {
+          if (hint) cp_async16_hint(dst + 32 * j, src + 32 * j, pol); else cp_async16(dst + 32 * j, src + 32 * j);
+        }
       }
       cp_async_commit();                   // always commit: keeps the group count uniform
     };
@@ -419,7 +435,9 @@ __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const i
           const float4* src = Xv + (size_t)cc * ldxv + lane;
           float4* dst = ring + (jn % D) * (CH * 32) + lane;
 #pragma unroll
-          for (int jj = 0; jj < CH; ++jj) cp_async16(dst + 32 * jj, src + 32 * jj);
+          for (int jj = 0; jj < CH; ++jj) {
+            if (hint) cp_async16_hint(dst + 32 * jj, src + 32 * jj, pol); else cp_async16(dst + 32 * jj, src + 32 * jj);
+          }
         }
         cp_async_commit();
       }
@@ -458,6 +476,58 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_pipe_kernel(const S
   extern __shared__ float4 s_ring[];
   if ((int)blockIdx.x < p.n_seg) spmm_hub_seg_cta<float4, CH, HAS_VAL>(p, (int)blockIdx.x, s_mem);
   else spmm_chunk_cta_pipe<CH, HAS_VAL, STATS>(p, (int)blockIdx.x - p.n_seg, s_mem, s_ring);
+}
+
+
+// ------------------------------------------------------------------ narrow rows (K <= 64 floats: e.g. the 40 logits)
+// A 160-byte row needs only 10 lanes.  Instead of folding several NEIGHBOURS of one row across the warp (which drains
+// at every row end and needs cross-group shuffles), each group of lanes takes its OWN ROW of the chunk: 3 rows
+// (K=40) advance concurrently per warp, each with 4 independent 128-bit gathers in flight, no shuffles at all.
+template <bool HAS_VAL>
+__device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const int cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lpr = p.nvec, groups = 32 / lpr;
+  const int g = lane / lpr, l = lane - g * lpr;
+  const bool active = g < groups;
+  const float4* Xv = reinterpret_cast<const float4*>(p.X);
+  float4* Yv = reinterpret_cast<float4*>(p.Y);
+  const size_t ldxv = (size_t)(p.ldx / 4), ldyv = (size_t)(p.ldy / 4);
+  const int chunk = cta * SPMM_WARPS + warp;
+  if (chunk >= p.n_chunks || !active) return;
+  const int row_lo = __ldg(p.chunk_rowptr + chunk), row_hi = __ldg(p.chunk_rowptr + chunk + 1);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bias4 = load_bias<float4>(p.bias, l);
+  for (int row = row_lo + g; row < row_hi; row += groups) {
+    const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+    const int deg = end - beg;
+    if (deg > p.hub_threshold) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {
+      int c[4]; float w[4]; float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + u); w[u] = HAS_VAL ? __ldg(p.val + e + u) : 1.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vfma(acc, w[u], x[u]);
+    }
+    for (; e < end; ++e) {
+      const int c = __ldg(p.col + e);
+      const float w = HAS_VAL ? __ldg(p.val + e) : 1.f;
+      vfma(acc, w, vldg(Xv + (size_t)c * ldxv + l));
+    }
+    if (p.mean) vdiv(acc, (float)max(deg, 1));
+    if (p.bias) vadd(acc, bias4);
+    Yv[(size_t)row * ldyv + l] = acc;
+  }
+}
+
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_narrow_kernel(const SpmmParams p) {
+  __shared__ float s_mem[SPMM_MAX_SLAB_FLOATS];
+  if ((int)blockIdx.x < p.n_seg) spmm_hub_seg_cta<float4, 1, HAS_VAL>(p, (int)blockIdx.x, s_mem);
+  else spmm_chunk_cta_narrow<HAS_VAL>(p, (int)blockIdx.x - p.n_seg);
 }
 
 // Sum a hub row's segment partials in segment order, apply the epilogue.
@@ -637,7 +707,7 @@ __global__ void __launch_bounds__(256) chunk_plan_kernel(const int32_t* __restri
 using namespace b200gnn;
 
 // 0 = automatic (pipelined kernel where eligible), 1 = always the register-staged kernel (tuning / A-B tests)
-static int g_spmm_variant = 0;
+static int g_spmm_variant = 0;  // 3 = pipelined without the L2 hint
 extern "C" void b200gnn_spmm_set_variant(int v) { g_spmm_variant = v; }
 
 extern "C" int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz, int32_t row_cost) {
@@ -703,6 +773,7 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   p.mean = reduce == B200GNN_REDUCE_MEAN;
   p.stream_store = (n_rows * K * 4 > (int64_t)64 << 20) ? 1 : 0;
   p.main_grid = (int32_t)((n_chunks + SPMM_WARPS - 1) / SPMM_WARPS);
+  p.l2_hint = (g_spmm_variant == 3) ? 0 : 1;     // variant 3: pipelined kernel without the L2 evict_last hint (A/B)
 
   // widest vector type the layout allows
   int W = 1;
@@ -720,7 +791,19 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   // variant 2 forces it for K=128 too.
   const bool pipe_ok = (W == 4) && g_spmm_variant != 1 &&
                        (p.nvec == 64 || p.nvec == 128 || (p.nvec == 32 && g_spmm_variant == 2));
-  if (pipe_ok && p.nvec == 32) rc = launch_spmm_pipe<1>(p, st);
+  const bool narrow_ok = (W == 4) && p.nvec <= 16 && !p.stat_partial && g_spmm_variant != 1;
+  if (narrow_ok) {
+    rc = B200GNN_OK;
+    const int grid = p.main_grid + p.n_seg;
+    if (p.val) spmm_rows_narrow_kernel<true><<<grid, SPMM_THREADS, 0, st>>>(p);
+    else spmm_rows_narrow_kernel<false><<<grid, SPMM_THREADS, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+    if (p.n_hub > 0) {
+      spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);
+      if ((rc = check_launch())) return rc;
+    }
+  }
+  else if (pipe_ok && p.nvec == 32) rc = launch_spmm_pipe<1>(p, st);
   else if (pipe_ok && p.nvec == 64) rc = launch_spmm_pipe<2>(p, st);
   else if (pipe_ok && p.nvec == 128) rc = launch_spmm_pipe<4>(p, st);
   else if (W == 4) rc = dispatch_ch<float4>(p, st);

@@ -35,6 +35,10 @@ from .engine import GCNStudentTrainer, gcn_norm, _is_symmetric
 from .sparse import SparseTensor, csr_graph_from
 
 
+import os as _os
+_DIAG_SKIP_COMM = _os.environ.get("B200GNN_DIAG_SKIP_ALLGATHER", "0") == "1"
+
+
 @dataclass
 class ShardPlan:
     """Host-side description of the partition (device-agnostic: also exercised on CPU with gloo)."""
@@ -156,6 +160,8 @@ class ShardedGCNTrainer(GCNStudentTrainer):
     # -- collectives
     def _all_gather(self, local: torch.Tensor) -> torch.Tensor:
         full = self.full[local.shape[1]]
+        if _DIAG_SKIP_COMM:            # timing diagnostics only (results are wrong): isolates the compute per rank
+            return full
         dist.all_gather_into_tensor(full, self._block_of(local), group=self.group)
         return full
 

@@ -77,3 +77,21 @@ def make_node_dataset(shape: dict = ARXIV, seed: int = 0, p_local: float = 0.0) 
     t_logits = torch.randn(N, Cn, generator=g) * 2.0
     t_feat = torch.relu(torch.randn(N, shape["teacher_dim"], generator=g))
     return NodeDataset(N, x, y, ei, split, Cn, t_logits, t_feat)
+
+
+# ogbn-mag shape (SURVEY.md §8d): node counts and directed relation sizes; reverse relations are added by the caller
+MAG_NODES = dict(paper=736_389, author=1_134_649, institution=8_740, field_of_study=59_965)
+MAG_RELATIONS = {("author", "affiliated_with", "institution"): 1_043_998,
+                 ("author", "writes", "paper"): 7_145_660,
+                 ("paper", "cites", "paper"): 5_416_271,
+                 ("paper", "has_topic", "field_of_study"): 7_505_078}
+
+
+def mag_relation_edges(src_type: str, dst_type: str, num_edges: int, seed: int) -> torch.Tensor:
+    """[2,E] (src, dst) for one relation: src uniform, dst skewed (u^3), duplicates removed (count approximate)."""
+    g = torch.Generator().manual_seed(seed)
+    ns, nd = MAG_NODES[src_type], MAG_NODES[dst_type]
+    src = torch.randint(0, ns, (num_edges,), generator=g)
+    dst = (torch.rand(num_edges, generator=g, dtype=torch.float64).pow(3) * nd).long().clamp_(max=nd - 1)
+    key = torch.unique(src * nd + dst)
+    return torch.stack([key // nd, key % nd])
