@@ -133,7 +133,10 @@ struct GatBwd {
   const float* el; const float* er;
   float* dpre;   // [nnz,H]  out: d loss / d (el[src]+er[dst])
   float* der;    // [n_rows,H] out (may be NULL when there is no er)
+  const int32_t* row_list;       // CTA kernel: rows to process (NULL: all rows)
+  const int32_t* chunk_rowptr;   // warp kernel: chunk plan
   int64_t ldf, ldd, n_rows;
+  int32_t n_list, n_chunks, hub_threshold;
   int32_t H, D, K;
   float slope;
 };
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd 
   __shared__ float s_tot[GAT_MAXH];
   __shared__ float s_der[GAT_WARPS][GAT_MAXH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t i = blockIdx.x; i < p.n_rows; i += gridDim.x) {
+  const int64_t n_items = p.row_list ? p.n_list : p.n_rows;
+  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int64_t i = p.row_list ? p.row_list[it] : it;
     const int b = p.rowptr[i], e = p.rowptr[i + 1];
     float Sh[GAT_MAXH];
 #pragma unroll
@@ -207,6 +212,85 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd 
       }
     }
     __syncthreads();
+  }
+}
+
+
+// Fast path: D % 4 == 0 and D/4 (lanes per head) a power of two <= 32 (D in {4,8,...,128}).  One warp per chunk of rows; per edge the
+// per-head dot product is a segmented xor-shuffle reduction over the D/4 lanes that hold that head; hub rows are
+// left to the CTA kernel above.
+constexpr int GAT_FJ = 8;   // float4 vectors per lane: K <= 1024
+__global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_warp_kernel(const GatBwd p) {
+  __shared__ float s_S[GAT_WARPS][GAT_MAXH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * GAT_WARPS + warp;
+  if (chunk >= p.n_chunks) return;
+  const int lph = p.D >> 2;                      // lanes per head
+  const int nvec = p.K >> 2, nj = (nvec + 31) >> 5;
+  const float4* F = reinterpret_cast<const float4*>(p.ft);
+  const float4* G = reinterpret_cast<const float4*>(p.dout);
+  const size_t ldfv = (size_t)(p.ldf >> 2), lddv = (size_t)(p.ldd >> 2);
+  int head[GAT_FJ];
+#pragma unroll
+  for (int j = 0; j < GAT_FJ; ++j) head[j] = (lane + 32 * j) / lph;
+  const int r0 = __ldg(p.chunk_rowptr + chunk), r1 = __ldg(p.chunk_rowptr + chunk + 1);
+  for (int i = r0; i < r1; ++i) {
+    const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
+    if (e - b > p.hub_threshold || b == e) {
+      if (b == e && p.der && lane < p.H) p.der[(size_t)i * p.H + lane] = 0.f;
+      continue;
+    }
+    float4 g[GAT_FJ];
+    float S[GAT_FJ];
+#pragma unroll
+    for (int j = 0; j < GAT_FJ; ++j) {
+      S[j] = 0.f;
+      g[j] = (j < nj && lane + 32 * j < nvec) ? __ldg(G + (size_t)i * lddv + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int k = b; k < e; ++k) {
+      const float4* f = F + (size_t)__ldg(p.col + k) * ldfv + lane;
+#pragma unroll
+      for (int j = 0; j < GAT_FJ; ++j) {
+        if (j < nj) {
+          float d = 0.f;
+          if (lane + 32 * j < nvec) { const float4 x = __ldg(f + 32 * j); d = x.x * g[j].x + x.y * g[j].y + x.z * g[j].z + x.w * g[j].w; }
+          for (int o = 1; o < lph; o <<= 1) d += __shfl_xor_sync(FULL_MASK, d, o);   // lph <= 32: stays inside the head's lanes
+          if (lane + 32 * j < nvec) {
+            const size_t o = (size_t)k * p.H + head[j];
+            if ((lane % lph) == 0) p.dpre[o] = d;
+            S[j] = fmaf(__ldg(p.a + o), d, S[j]);
+          }
+        }
+      }
+    }
+    // per-head totals: each head lives in one aligned group of lph lanes of one chunk j; its leader publishes S
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < GAT_FJ; ++j)
+      if (j < nj && lane + 32 * j < nvec && (lane % lph) == 0) s_S[warp][head[j]] = S[j];
+    __syncwarp();
+    float dr[GAT_MAXH];
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h) dr[h] = 0.f;
+    for (int k = b + lane; k < e; k += 32) {
+      const int src = __ldg(p.col + k);
+#pragma unroll
+      for (int h = 0; h < GAT_MAXH; ++h)
+        if (h < p.H) {
+          const size_t o = (size_t)k * p.H + h;
+          const float de = p.a[o] * (p.dpre[o] - s_S[warp][h]);
+          const float pre = p.el[(size_t)src * p.H + h] + (p.er ? p.er[(size_t)i * p.H + h] : 0.f);
+          const float dp = pre > 0.f ? de : de * p.slope;
+          p.dpre[o] = dp;
+          dr[h] += dp;
+        }
+    }
+    if (p.der) {
+#pragma unroll
+      for (int h = 0; h < GAT_MAXH; ++h)
+        if (h < p.H) { const float t = gsum(dr[h]); if (lane == 0) p.der[(size_t)i * p.H + h] = t; }
+    }
+    __syncwarp();
   }
 }
 
@@ -284,7 +368,9 @@ extern "C" int b200gnn_gat_aggregate_f32(const int32_t* rowptr, const int32_t* c
 
 extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const float* a, const float* ft, int64_t ldf,
                                         const float* dout, int64_t ldd, const float* el, const float* er, int64_t n_rows,
-                                        int64_t H, int64_t D, float negative_slope, float* dpre, float* der, void* stream) {
+                                        int64_t H, int64_t D, float negative_slope, float* dpre, float* der,
+                                        const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
+                                        const int32_t* hub_rows, int64_t n_hub, void* stream) {
   if (!rowptr || !a || !ft || !dout || !el || !dpre || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < H * D ||
       ldd < H * D)
     return B200GNN_ERR_BAD_ARG;
@@ -293,8 +379,26 @@ extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* co
   p.rowptr = rowptr; p.col = col; p.a = a; p.ft = ft; p.dout = dout; p.el = el; p.er = er; p.dpre = dpre; p.der = der;
   p.ldf = ldf; p.ldd = ldd; p.n_rows = n_rows; p.H = (int32_t)H; p.D = (int32_t)D; p.K = (int32_t)(H * D);
   p.slope = negative_slope;
+  p.row_list = nullptr; p.chunk_rowptr = chunk_rowptr; p.n_list = 0; p.n_chunks = (int32_t)n_chunks;
+  p.hub_threshold = hub_threshold;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t lph = D / 4;
+  const bool fast = chunk_rowptr && n_chunks > 0 && D % 4 == 0 && (lph & (lph - 1)) == 0 && H * D <= 4 * 32 * GAT_FJ &&
+                    ldf % 4 == 0 && ldd % 4 == 0 && aligned_to(ft, 16) && aligned_to(dout, 16) && (n_hub == 0 || hub_rows) &&
+                    lph <= 32;
+  int rc;
+  if (fast) {
+    gat_bwd_rows_warp_kernel<<<(int)((n_chunks + GAT_WARPS - 1) / GAT_WARPS), GAT_THREADS, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+    if (n_hub > 0) {
+      p.row_list = hub_rows; p.n_list = (int32_t)n_hub;
+      gat_bwd_rows_kernel<<<(int)n_hub, GAT_THREADS, 0, st>>>(p);
+      if ((rc = check_launch())) return rc;
+    }
+    return B200GNN_OK;
+  }
   int64_t grid = n_rows < 148 * 32 ? n_rows : 148 * 32;
-  gat_bwd_rows_kernel<<<(int)grid, GAT_THREADS, 0, (cudaStream_t)stream>>>(p);
+  gat_bwd_rows_kernel<<<(int)grid, GAT_THREADS, 0, st>>>(p);
   return check_launch();
 }
 

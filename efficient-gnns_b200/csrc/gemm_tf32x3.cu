@@ -33,7 +33,9 @@ constexpr int THREADS = 384;
 constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (A and B tiles are both 128 x 32 fp32)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024 B alignment
+constexpr int EPI_LD = 36;                              // floats per staged row (144 B: 16-byte aligned, conflict-free)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // one 32x32 staging block per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + slack for 1024 B alignment
 constexpr int TMEM_COLS = ACC_STAGES * BN;              // 256
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
@@ -71,6 +73,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* acc_full = bars + 3 * STAGES;     // accumulator ready     [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;  // accumulator drained [ACC_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -179,24 +182,33 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), r);
         const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float* dst = p.C + (size_t)row * p.ldc + col0;
-          if (vec_ok && col0 + 32 <= p.N) {
+        if (vec_ok && col0 + 32 <= p.N) {
+          // Transpose the warp's 32x32 block through shared memory so that global stores are whole 128-byte row
+          // segments (4 rows x 128 B per instruction) instead of 32 scattered 16-byte pieces.
+          float* tile = epi_smem + (warp - 8) * (32 * EPI_LD);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (p.bias) {
-                v.x += __ldg(p.bias + col0 + j); v.y += __ldg(p.bias + col0 + j + 1);
-                v.z += __ldg(p.bias + col0 + j + 2); v.w += __ldg(p.bias + col0 + j + 3);
-              }
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          } else {
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tile + lane * EPI_LD + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+          const int sub = lane >> 3, cq = (lane & 7) * 4;     // 4 rows per instruction, 8 lanes x float4 per row
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = make_float4(__ldg(p.bias + col0 + cq), __ldg(p.bias + col0 + cq + 1), __ldg(p.bias + col0 + cq + 2),
+                                       __ldg(p.bias + col0 + cq + 3));
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            const int grow = m0 + q * 32 + rr;
+            float4 v = *reinterpret_cast<const float4*>(tile + rr * EPI_LD + cq);
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (grow < p.M) *reinterpret_cast<float4*>(p.C + (size_t)grow * p.ldc + col0 + cq) = v;
           }
+          __syncwarp();
+        } else if (row < p.M && col0 < p.N) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
         }
       }
       tc_fence_before();

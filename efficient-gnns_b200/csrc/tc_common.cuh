@@ -79,11 +79,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // x - hi is exact in fp32, so hi + lo reproduces x to ~2^-22 relative with a ZERO-MEAN error.  (Truncating instead
 // of rounding leaves every product biased towards zero by ~5e-7; the bias survives the long, heavily cancelling
 // sums of the backward pass and showed up as 1e-4-level errors in the early-layer weight gradients.)
-__device__ __forceinline__ uint32_t rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away from zero) to the 10-bit tf32 mantissa, on the integer pipe: add half an ulp of the
+// kept field to the magnitude bits and clear the 13 dropped bits (same result as cvt.rna.tf32.f32 for finite inputs,
+// at full instead of quarter issue rate — the splitter warps sit between TMA and MMA on the critical path).
+__device__ __forceinline__ uint32_t rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & TF32_MASK; }
 __device__ __forceinline__ void split1(uint32_t v, uint32_t& h, uint32_t& l) {
   h = rna_tf32(__uint_as_float(v));
   l = rna_tf32(__uint_as_float(v) - __uint_as_float(h));

@@ -272,7 +272,9 @@ class _GatAggregate(torch.autograd.Function):
         lib.check(L.b200gnn_gat_bwd_rows_f32(G.rowptr.data_ptr(), G.col.data_ptr(), a.data_ptr(), ft.data_ptr(), ft.stride(0),
                                              dout.data_ptr(), dout.stride(0), el.data_ptr(),
                                              None if er is None else er.data_ptr(), G.n_rows, H, D, ctx.slope, dpre.data_ptr(),
-                                             None if der is None else der.data_ptr(), s), "gat_bwd_rows_f32")
+                                             None if der is None else der.data_ptr(), G.chunk_rowptr.data_ptr(), G.n_chunks,
+                                             G.hub_threshold, G.hub_rows.data_ptr() if G.n_hub else None, G.n_hub, s),
+                  "gat_bwd_rows_f32")
         Gt = st.engine_csc("value")                              # transposed graph as CSR (rows = sources)
         perm = _csr2csc_i32(st)
         dft = torch.empty(Gt.n_rows, H * D, dtype=torch.float32, device=ft.device)

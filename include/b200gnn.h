@@ -330,7 +330,9 @@ int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const fl
                              int64_t ldd, const float* el, const float* er,
                              int64_t n_rows, int64_t H, int64_t D,
                              float negative_slope, float* dpre, float* der,
-                             void* stream);
+                             const int32_t* chunk_rowptr, int64_t n_chunks,
+                             int32_t hub_threshold, const int32_t* hub_rows,
+                             int64_t n_hub, void* stream);
 int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx,
                                   const float* vals, int64_t n_rows, int64_t H,
                                   float* out, void* stream);
