@@ -6,13 +6,19 @@
 // Forward : gat_edge_softmax (a[nnz,H]) + gat_aggregate (also used for d ft on the transposed graph through `eidx`).
 // Backward: gat_bwd_rows (per destination: d a = <ft[src], d out[dst]> per head, softmax + leaky-relu backward,
 //           d er, d pre[nnz,H]) + gat_segment_sum (d el over the transposed graph).
-// Work split: one warp per chunk of rows (the SpMM chunk plan); rows above hub_threshold are taken by whole CTAs
-// (8 warps stride over the edges, fixed-order shared-memory reduction) — no atomics, deterministic.
+// Work split.  Row-wide kernels (aggregate, bwd_rows): one warp per chunk of rows (the SpMM chunk plan); lanes own
+// vectors lane+32j of the K-float row and U edges are loaded before they are consumed, so U*NJ independent row
+// gathers are in flight per warp.  Rows above hub_threshold go to one 512-thread CTA each (16 warps stride over
+// groups of U edges, partials combined in warp order through shared memory).  Scalar kernels (edge softmax,
+// segment sum): lanes stride over a row's edges and carry all H heads at once; rows above GAT_CTA_DEG are taken
+// by the whole CTA.  No atomics anywhere: every sum has a fixed order.
 #include "common.cuh"
 
 namespace b200gnn {
 
 constexpr int GAT_THREADS = 256, GAT_WARPS = 8, GAT_MAXH = 16, GAT_MAXJ = 12;
+constexpr int GAT_HUB_THREADS = 512, GAT_HUB_WARPS = 16;
+constexpr int GAT_CTA_DEG = 512;
 
 __device__ __forceinline__ float gsum(float v) {
 #pragma unroll
@@ -25,30 +31,138 @@ __device__ __forceinline__ float gmax(float v) {
   return v;
 }
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+__device__ __forceinline__ float vdot(const float& a, const float& b) { return a * b; }
+__device__ __forceinline__ float vdot(const float2& a, const float2& b) { return fmaf(a.x, b.x, a.y * b.y); }
+__device__ __forceinline__ float vdot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// per-head reduction over the group that owns a row: a warp (shuffles) or the 8-warp CTA (shuffles + shared memory,
+// combined in warp order).  Every thread of the group gets the result.
+template <bool CTA, bool MAX>
+__device__ __forceinline__ void reduce_heads(float (&v)[GAT_MAXH], int H, float (*s_red)[GAT_MAXH], int lane, int warp) {
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h)
+    if (h < H) v[h] = MAX ? gmax(v[h]) : gsum(v[h]);
+  if (CTA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < GAT_MAXH; ++h)
+        if (h < H) s_red[warp][h] = v[h];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < H) {
+        float t = s_red[0][h];
+        for (int w = 1; w < GAT_WARPS; ++w) t = MAX ? fmaxf(t, s_red[w][h]) : t + s_red[w][h];
+        v[h] = t;
+      }
+    __syncthreads();
+  }
+}
 
 // ---------------------------------------------------------------- edge softmax: a[e,h]
-// one warp per destination row; lanes stride over the row's edges; three cheap passes over scalars.
-__global__ void __launch_bounds__(GAT_THREADS) gat_edge_softmax_kernel(
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ el,
-    const float* __restrict__ er, int H, float slope, float eps, int64_t n_rows, float* __restrict__ a) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t i = (int64_t)blockIdx.x * GAT_WARPS + (threadIdx.x >> 5); i < n_rows; i += (int64_t)gridDim.x * GAT_WARPS) {
-    const int b = rowptr[i], e = rowptr[i + 1];
-    if (b == e) continue;
-    for (int h = 0; h < H; ++h) {
-      const float r = er ? er[(size_t)i * H + h] : 0.f;
-      float m = -INFINITY;
-      for (int k = b + lane; k < e; k += 32) m = fmaxf(m, lrelu(el[(size_t)col[k] * H + h] + r, slope));
-      m = gmax(m);
-      float s = 0.f;
-      for (int k = b + lane; k < e; k += 32) s += expf(lrelu(el[(size_t)col[k] * H + h] + r, slope) - m);
-      s = gsum(s) + eps;
-      for (int k = b + lane; k < e; k += 32)
-        a[(size_t)k * H + h] = expf(lrelu(el[(size_t)col[k] * H + h] + r, slope) - m) / s;
+struct GatSoftmax {
+  const int32_t* rowptr; const int32_t* col; const float* el; const float* er; float* a;
+  int64_t n_rows; int32_t H; float slope, eps;
+};
+
+template <bool CTA>
+__device__ __forceinline__ void softmax_row(const GatSoftmax& p, int64_t i, int b, int e, int tid, int nt,
+                                            float (*s_red)[GAT_MAXH], int lane, int warp) {
+  float r[GAT_MAXH], m[GAT_MAXH], s[GAT_MAXH];
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) {
+    r[h] = (p.er && h < p.H) ? __ldg(p.er + (size_t)i * p.H + h) : 0.f;
+    m[h] = -INFINITY;
+    s[h] = 0.f;
+  }
+  for (int k = b + tid; k < e; k += nt) {
+    const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) m[h] = fmaxf(m[h], lrelu(__ldg(x + h) + r[h], p.slope));
+  }
+  reduce_heads<CTA, true>(m, p.H, s_red, lane, warp);
+  for (int k = b + tid; k < e; k += nt) {
+    const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) s[h] += expf(lrelu(__ldg(x + h) + r[h], p.slope) - m[h]);
+  }
+  reduce_heads<CTA, false>(s, p.H, s_red, lane, warp);
+  for (int k = b + tid; k < e; k += nt) {
+    const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) p.a[(size_t)k * p.H + h] = expf(lrelu(__ldg(x + h) + r[h], p.slope) - m[h]) / (s[h] + p.eps);
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS) gat_edge_softmax_kernel(const GatSoftmax p) {
+  __shared__ float s_red[GAT_WARPS][GAT_MAXH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r0 = (int64_t)blockIdx.x * GAT_WARPS; r0 < p.n_rows; r0 += (int64_t)gridDim.x * GAT_WARPS) {
+    const int64_t i = r0 + warp;
+    if (i < p.n_rows) {
+      const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
+      if (e > b && e - b <= GAT_CTA_DEG) softmax_row<false>(p, i, b, e, lane, 32, s_red, lane, warp);
+    }
+    for (int w = 0; w < GAT_WARPS; ++w) {          // same decision in every thread of the CTA
+      const int64_t r = r0 + w;
+      if (r >= p.n_rows) break;
+      const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
+      if (e - b > GAT_CTA_DEG) softmax_row<true>(p, r, b, e, threadIdx.x, GAT_THREADS, s_red, lane, warp);
     }
   }
 }
 
+// ---------------------------------------------------------------- out[j,h] = sum_k vals[eidx[k], h]   (d el)
+struct GatSegSum {
+  const int32_t* rowptr; const int32_t* eidx; const float* vals; float* out;
+  int64_t n_rows; int32_t H;
+};
+
+template <bool CTA>
+__device__ __forceinline__ void segsum_row(const GatSegSum& p, int64_t j, int b, int e, int tid, int nt,
+                                           float (*s_red)[GAT_MAXH], int lane, int warp) {
+  float s[GAT_MAXH];
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) s[h] = 0.f;
+  for (int k = b + tid; k < e; k += nt) {
+    const float* x = p.vals + (size_t)(p.eidx ? __ldg(p.eidx + k) : k) * p.H;
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) s[h] += __ldg(x + h);
+  }
+  reduce_heads<CTA, false>(s, p.H, s_red, lane, warp);
+  if (tid == 0) {
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) p.out[(size_t)j * p.H + h] = s[h];
+  }
+}
+
+__global__ void __launch_bounds__(GAT_THREADS) gat_segment_sum_kernel(const GatSegSum p) {
+  __shared__ float s_red[GAT_WARPS][GAT_MAXH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r0 = (int64_t)blockIdx.x * GAT_WARPS; r0 < p.n_rows; r0 += (int64_t)gridDim.x * GAT_WARPS) {
+    const int64_t j = r0 + warp;
+    if (j < p.n_rows) {
+      const int b = __ldg(p.rowptr + j), e = __ldg(p.rowptr + j + 1);
+      if (e - b <= GAT_CTA_DEG) segsum_row<false>(p, j, b, e, lane, 32, s_red, lane, warp);
+    }
+    for (int w = 0; w < GAT_WARPS; ++w) {
+      const int64_t r = r0 + w;
+      if (r >= p.n_rows) break;
+      const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
+      if (e - b > GAT_CTA_DEG) segsum_row<true>(p, r, b, e, threadIdx.x, GAT_THREADS, s_red, lane, warp);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- aggregate
 struct GatAgg {
   const int32_t* rowptr; const int32_t* col; const int32_t* eidx;   // eidx: position of edge k in a[] (NULL: k)
   const int32_t* chunk_rowptr; const int32_t* hub_rows;
@@ -57,74 +171,92 @@ struct GatAgg {
   int32_t n_chunks, n_hub, hub_threshold, H, D, K;
 };
 
-// per-lane column map: lane handles vectors v = lane + 32*j (j < nj) of width W; head of vector v = (v*W)/D
-template <typename V>
-__device__ __forceinline__ void agg_edges(const GatAgg& p, int beg, int end, int stride, int first, int lane, int nj,
-                                          V (&acc)[GAT_MAXJ]) {
+// lane handles vectors v = lane + 32*j (j < NJ) of width W; head of vector v = (v*W)/D.  The group's warps take
+// groups of U consecutive edges: warp `first` of `stride` warps starts at beg + first*U.
+template <typename V, int NJ, int U>
+__device__ __forceinline__ void agg_edges(const GatAgg& p, int beg, int end, int first, int stride, int lane, int nvec,
+                                          const int (&head)[NJ], V (&acc)[NJ]) {
   constexpr int W = VecTraits<V>::W;
   const V* F = reinterpret_cast<const V*>(p.ft);
   const size_t ldv = (size_t)(p.ldf / W);
-  int head[GAT_MAXJ];
+  for (int k0 = beg + first * U; k0 < end; k0 += stride * U) {
+    V x[U][NJ];
+    float w[U][NJ];
 #pragma unroll
-  for (int j = 0; j < GAT_MAXJ; ++j) head[j] = ((lane + 32 * j) * W) / p.D;
-  for (int k = beg + first; k < end; k += stride) {
-    const int src = __ldg(p.col + k);
-    const size_t ak = (size_t)(p.eidx ? __ldg(p.eidx + k) : k) * p.H;
-    const V* row = F + (size_t)src * ldv + lane;
+    for (int u = 0; u < U; ++u) {
+      const int kk = k0 + u;
+      if (kk < end) {
+        const V* row = F + (size_t)__ldg(p.col + kk) * ldv + lane;
+        const float* ak = p.a + (size_t)(p.eidx ? __ldg(p.eidx + kk) : kk) * p.H;
 #pragma unroll
-    for (int j = 0; j < GAT_MAXJ; ++j)
-      if (j < nj && (lane + 32 * j) * W < p.K) vfma(acc[j], __ldg(p.a + ak + head[j]), vldg(row + 32 * j));
+        for (int j = 0; j < NJ; ++j) {
+          if (lane + 32 * j < nvec) { x[u][j] = vldg(row + 32 * j); w[u][j] = __ldg(ak + head[j]); }
+          else { vzero(x[u][j]); w[u][j] = 0.f; }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { vzero(x[u][j]); w[u][j] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) vfma(acc[j], w[u][j], x[u][j]);
   }
 }
 
-template <typename V>
+template <typename V, int NJ, int U>
 __global__ void __launch_bounds__(GAT_THREADS) gat_aggregate_kernel(const GatAgg p) {
   constexpr int W = VecTraits<V>::W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = p.K / W, nj = (nvec + 31) / 32;
+  const int nvec = p.K / W;
   V* O = reinterpret_cast<V*>(p.out);
   const size_t ldov = (size_t)(p.ldo / W);
   const int chunk = blockIdx.x * GAT_WARPS + warp;
   if (chunk >= p.n_chunks) return;
+  int head[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) head[j] = ((lane + 32 * j) * W) / p.D;
   const int r0 = __ldg(p.chunk_rowptr + chunk), r1 = __ldg(p.chunk_rowptr + chunk + 1);
   for (int r = r0; r < r1; ++r) {
     const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
     if (e - b > p.hub_threshold) continue;
-    V acc[GAT_MAXJ];
+    V acc[NJ];
 #pragma unroll
-    for (int j = 0; j < GAT_MAXJ; ++j) vzero(acc[j]);
-    agg_edges<V>(p, b, e, 1, 0, lane, nj, acc);
+    for (int j = 0; j < NJ; ++j) vzero(acc[j]);
+    agg_edges<V, NJ, U>(p, b, e, 0, 1, lane, nvec, head, acc);
 #pragma unroll
-    for (int j = 0; j < GAT_MAXJ; ++j)
-      if (j < nj && lane + 32 * j < nvec) O[(size_t)r * ldov + lane + 32 * j] = acc[j];
+    for (int j = 0; j < NJ; ++j)
+      if (lane + 32 * j < nvec) O[(size_t)r * ldov + lane + 32 * j] = acc[j];
   }
 }
 
-// one CTA per hub row: warps stride over the edges, partials combined in warp order through shared memory
-template <typename V>
-__global__ void __launch_bounds__(GAT_THREADS) gat_aggregate_hub_kernel(const GatAgg p) {
+// one CTA per hub row: warps stride over groups of U edges, partials combined in warp order through shared memory
+template <typename V, int NJ, int U>
+__global__ void __launch_bounds__(GAT_HUB_THREADS) gat_aggregate_hub_kernel(const GatAgg p) {
   constexpr int W = VecTraits<V>::W;
   extern __shared__ float s_row[];   // K floats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = p.K / W, nj = (nvec + 31) / 32;
+  const int nvec = p.K / W;
   const int r = __ldg(p.hub_rows + blockIdx.x);
   const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
-  V acc[GAT_MAXJ];
+  int head[NJ];
+  V acc[NJ];
 #pragma unroll
-  for (int j = 0; j < GAT_MAXJ; ++j) vzero(acc[j]);
-  agg_edges<V>(p, b, e, GAT_WARPS, warp, lane, nj, acc);
-  for (int i = threadIdx.x; i < p.K; i += GAT_THREADS) s_row[i] = 0.f;
+  for (int j = 0; j < NJ; ++j) { head[j] = ((lane + 32 * j) * W) / p.D; vzero(acc[j]); }
+  agg_edges<V, NJ, U>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, head, acc);
+  for (int i = threadIdx.x; i < p.K; i += GAT_HUB_THREADS) s_row[i] = 0.f;
   __syncthreads();
   V* sv = reinterpret_cast<V*>(s_row);
-  for (int w = 0; w < GAT_WARPS; ++w) {
+  for (int w = 0; w < GAT_HUB_WARPS; ++w) {
     if (warp == w) {
 #pragma unroll
-      for (int j = 0; j < GAT_MAXJ; ++j)
-        if (j < nj && lane + 32 * j < nvec) { V t = sv[lane + 32 * j]; vadd(t, acc[j]); sv[lane + 32 * j] = t; }
+      for (int j = 0; j < NJ; ++j)
+        if (lane + 32 * j < nvec) { V t = sv[lane + 32 * j]; vadd(t, acc[j]); sv[lane + 32 * j] = t; }
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < p.K; i += GAT_THREADS) p.out[(size_t)r * p.ldo + i] = s_row[i];
+  for (int i = threadIdx.x; i < p.K; i += GAT_HUB_THREADS) p.out[(size_t)r * p.ldo + i] = s_row[i];
 }
 
 // ---------------------------------------------------------------- backward, per destination row
@@ -133,179 +265,167 @@ struct GatBwd {
   const float* el; const float* er;
   float* dpre;   // [nnz,H]  out: d loss / d (el[src]+er[dst])
   float* der;    // [n_rows,H] out (may be NULL when there is no er)
-  const int32_t* row_list;       // CTA kernel: rows to process (NULL: all rows)
-  const int32_t* chunk_rowptr;   // warp kernel: chunk plan
+  const int32_t* chunk_rowptr; const int32_t* hub_rows;
   int64_t ldf, ldd, n_rows;
-  int32_t n_list, n_chunks, hub_threshold;
+  int32_t n_chunks, n_hub, hub_threshold;
   int32_t H, D, K;
   float slope;
 };
 
-// One CTA per destination row (rows are cheap on average; a CTA gives hubs 8 warps).  Phase 1: d a[e,h] =
-// <ft[src,h,:], dout[dst,h,:]> (warp per edge, per-head warp reductions), phase 2: softmax and leaky-relu backward.
-__global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd p) {
-  __shared__ float s_S[GAT_WARPS][GAT_MAXH];
-  __shared__ float s_tot[GAT_MAXH];
-  __shared__ float s_der[GAT_WARPS][GAT_MAXH];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n_items = p.row_list ? p.n_list : p.n_rows;
-  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int64_t i = p.row_list ? p.row_list[it] : it;
-    const int b = p.rowptr[i], e = p.rowptr[i + 1];
-    float Sh[GAT_MAXH];
+// phase 1 over a group's share of the row's edges: d a[k,h] = <ft[src,h,:], dout[i,h,:]> staged in dpre, and the
+// group-local S[h] += a[k,h] * d a[k,h] (same value on every lane).
+template <typename V, int NJ, int U>
+__device__ __forceinline__ void bwd_edges(const GatBwd& p, int beg, int end, int first, int stride, int lane, int nvec,
+                                          const V (&g)[NJ], const int (&head)[NJ], float (&S)[GAT_MAXH]) {
+  constexpr int W = VecTraits<V>::W;
+  const V* F = reinterpret_cast<const V*>(p.ft);
+  const size_t ldv = (size_t)(p.ldf / W);
+  for (int k0 = beg + first * U; k0 < end; k0 += stride * U) {
+    V x[U][NJ];
 #pragma unroll
-    for (int h = 0; h < GAT_MAXH; ++h) Sh[h] = 0.f;
-    const float* g = p.dout + (size_t)i * p.ldd;
-    for (int k = b + warp; k < e; k += GAT_WARPS) {
-      const float* f = p.ft + (size_t)p.col[k] * p.ldf;
-      float part[GAT_MAXH];
+    for (int u = 0; u < U; ++u) {
+      const int kk = k0 + u;
+      if (kk < end) {
+        const V* row = F + (size_t)__ldg(p.col + kk) * ldv + lane;
 #pragma unroll
-      for (int h = 0; h < GAT_MAXH; ++h) part[h] = 0.f;
-      for (int c = lane; c < p.K; c += 32) {
-        const float v = __ldg(f + c) * __ldg(g + c);
-        const int h = c / p.D;
-#pragma unroll
-        for (int hh = 0; hh < GAT_MAXH; ++hh) part[hh] += (hh == h) ? v : 0.f;
-      }
-#pragma unroll
-      for (int h = 0; h < GAT_MAXH; ++h)
-        if (h < p.H) {
-          const float da = gsum(part[h]);
-          if (lane == 0) p.dpre[(size_t)k * p.H + h] = da;          // staged: d a
-          Sh[h] += p.a[(size_t)k * p.H + h] * da;                   // same value on every lane
+        for (int j = 0; j < NJ; ++j) {
+          if (lane + 32 * j < nvec) x[u][j] = vldg(row + 32 * j);
+          else vzero(x[u][j]);
         }
-    }
-    if (lane == 0)
-      for (int h = 0; h < p.H; ++h) s_S[warp][h] = Sh[h];
-    __syncthreads();
-    if (threadIdx.x < p.H) {
-      float t = 0.f;
-      for (int w = 0; w < GAT_WARPS; ++w) t += s_S[w][threadIdx.x];
-      s_tot[threadIdx.x] = t;
-    }
-    __syncthreads();
-    // phase 2: d e = a (d a - S);  d pre = d e * leaky'(pre);  d er[i,h] = sum_e d pre
-    float dr[GAT_MAXH];
+      } else {
 #pragma unroll
-    for (int h = 0; h < GAT_MAXH; ++h) dr[h] = 0.f;
-    for (int k = b + threadIdx.x; k < e; k += GAT_THREADS) {
-      const int src = p.col[k];
-      for (int h = 0; h < p.H; ++h) {
-        const size_t o = (size_t)k * p.H + h;
-        const float de = p.a[o] * (p.dpre[o] - s_tot[h]);
-        const float pre = p.el[(size_t)src * p.H + h] + (p.er ? p.er[(size_t)i * p.H + h] : 0.f);
-        const float dp = pre > 0.f ? de : de * p.slope;
-        p.dpre[o] = dp;
-        dr[h] += dp;
+        for (int j = 0; j < NJ; ++j) vzero(x[u][j]);
       }
     }
-    if (p.der) {
-      for (int h = 0; h < p.H; ++h) {
-        const float t = gsum(dr[h]);
-        if (lane == 0) s_der[warp][h] = t;
-      }
-      __syncthreads();
-      if (threadIdx.x < p.H) {
-        float t = 0.f;
-        for (int w = 0; w < GAT_WARPS; ++w) t += s_der[w][threadIdx.x];
-        p.der[(size_t)i * p.H + threadIdx.x] = t;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int kk = k0 + u;
+      if (kk < end) {
+        float d[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) d[j] = vdot(x[u][j], g[j]);
+#pragma unroll
+        for (int h = 0; h < GAT_MAXH; ++h)
+          if (h < p.H) {
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) part += (head[j] == h) ? d[j] : 0.f;
+            const float da = gsum(part);
+            const size_t o = (size_t)kk * p.H + h;
+            if (lane == 0) p.dpre[o] = da;
+            S[h] = fmaf(__ldg(p.a + o), da, S[h]);
+          }
       }
     }
-    __syncthreads();
   }
 }
 
+// phase 2: d e = a (d a - S);  d pre = d e * leaky'(pre);  dr[h] = this thread's share of d er[i,h]
+__device__ __forceinline__ void bwd_phase2(const GatBwd& p, int64_t i, int b, int e, int tid, int nt,
+                                           const float (&S)[GAT_MAXH], float (&dr)[GAT_MAXH]) {
+  float r[GAT_MAXH];
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) {
+    r[h] = (p.er && h < p.H) ? __ldg(p.er + (size_t)i * p.H + h) : 0.f;
+    dr[h] = 0.f;
+  }
+  for (int k = b + tid; k < e; k += nt) {
+    const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) {
+        const size_t o = (size_t)k * p.H + h;
+        const float de = p.a[o] * (p.dpre[o] - S[h]);
+        const float dp = (__ldg(x + h) + r[h]) > 0.f ? de : de * p.slope;
+        p.dpre[o] = dp;
+        dr[h] += dp;
+      }
+  }
+}
 
-// Fast path: D % 4 == 0 and D/4 (lanes per head) a power of two <= 32 (D in {4,8,...,128}).  One warp per chunk of rows; per edge the
-// per-head dot product is a segmented xor-shuffle reduction over the D/4 lanes that hold that head; hub rows are
-// left to the CTA kernel above.
-constexpr int GAT_FJ = 8;   // float4 vectors per lane: K <= 1024
-__global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_warp_kernel(const GatBwd p) {
-  __shared__ float s_S[GAT_WARPS][GAT_MAXH];
+template <typename V, int NJ, int U>
+__global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd p) {
+  constexpr int W = VecTraits<V>::W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = blockIdx.x * GAT_WARPS + warp;
   if (chunk >= p.n_chunks) return;
-  const int lph = p.D >> 2;                      // lanes per head
-  const int nvec = p.K >> 2, nj = (nvec + 31) >> 5;
-  const float4* F = reinterpret_cast<const float4*>(p.ft);
-  const float4* G = reinterpret_cast<const float4*>(p.dout);
-  const size_t ldfv = (size_t)(p.ldf >> 2), lddv = (size_t)(p.ldd >> 2);
-  int head[GAT_FJ];
+  const int nvec = p.K / W;
+  const V* G = reinterpret_cast<const V*>(p.dout);
+  const size_t lddv = (size_t)(p.ldd / W);
+  int head[NJ];
 #pragma unroll
-  for (int j = 0; j < GAT_FJ; ++j) head[j] = (lane + 32 * j) / lph;
+  for (int j = 0; j < NJ; ++j) head[j] = ((lane + 32 * j) * W) / p.D;
   const int r0 = __ldg(p.chunk_rowptr + chunk), r1 = __ldg(p.chunk_rowptr + chunk + 1);
   for (int i = r0; i < r1; ++i) {
     const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
-    if (e - b > p.hub_threshold || b == e) {
-      if (b == e && p.der && lane < p.H) p.der[(size_t)i * p.H + lane] = 0.f;
-      continue;
+    if (e - b > p.hub_threshold) continue;
+    V g[NJ];
+    float S[GAT_MAXH], dr[GAT_MAXH];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (lane + 32 * j < nvec) g[j] = vldg(G + (size_t)i * lddv + lane + 32 * j);
+      else vzero(g[j]);
     }
-    float4 g[GAT_FJ];
-    float S[GAT_FJ];
 #pragma unroll
-    for (int j = 0; j < GAT_FJ; ++j) {
-      S[j] = 0.f;
-      g[j] = (j < nj && lane + 32 * j < nvec) ? __ldg(G + (size_t)i * lddv + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int k = b; k < e; ++k) {
-      const float4* f = F + (size_t)__ldg(p.col + k) * ldfv + lane;
-#pragma unroll
-      for (int j = 0; j < GAT_FJ; ++j) {
-        if (j < nj) {
-          float d = 0.f;
-          if (lane + 32 * j < nvec) { const float4 x = __ldg(f + 32 * j); d = x.x * g[j].x + x.y * g[j].y + x.z * g[j].z + x.w * g[j].w; }
-          for (int o = 1; o < lph; o <<= 1) d += __shfl_xor_sync(FULL_MASK, d, o);   // lph <= 32: stays inside the head's lanes
-          if (lane + 32 * j < nvec) {
-            const size_t o = (size_t)k * p.H + head[j];
-            if ((lane % lph) == 0) p.dpre[o] = d;
-            S[j] = fmaf(__ldg(p.a + o), d, S[j]);
-          }
-        }
-      }
-    }
-    // per-head totals: each head lives in one aligned group of lph lanes of one chunk j; its leader publishes S
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < GAT_FJ; ++j)
-      if (j < nj && lane + 32 * j < nvec && (lane % lph) == 0) s_S[warp][head[j]] = S[j];
-    __syncwarp();
-    float dr[GAT_MAXH];
-#pragma unroll
-    for (int h = 0; h < GAT_MAXH; ++h) dr[h] = 0.f;
-    for (int k = b + lane; k < e; k += 32) {
-      const int src = __ldg(p.col + k);
-#pragma unroll
-      for (int h = 0; h < GAT_MAXH; ++h)
-        if (h < p.H) {
-          const size_t o = (size_t)k * p.H + h;
-          const float de = p.a[o] * (p.dpre[o] - s_S[warp][h]);
-          const float pre = p.el[(size_t)src * p.H + h] + (p.er ? p.er[(size_t)i * p.H + h] : 0.f);
-          const float dp = pre > 0.f ? de : de * p.slope;
-          p.dpre[o] = dp;
-          dr[h] += dp;
-        }
-    }
+    for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
+    bwd_edges<V, NJ, U>(p, b, e, 0, 1, lane, nvec, g, head, S);
+    __syncwarp();                                   // lane 0's staged d a is read by every lane below
+    bwd_phase2(p, i, b, e, lane, 32, S, dr);
     if (p.der) {
 #pragma unroll
       for (int h = 0; h < GAT_MAXH; ++h)
         if (h < p.H) { const float t = gsum(dr[h]); if (lane == 0) p.der[(size_t)i * p.H + h] = t; }
     }
-    __syncwarp();
   }
 }
 
-// out[j,h] = sum over rows' edges k of vals[eidx[k], h]   (d el over the transposed graph)
-__global__ void __launch_bounds__(GAT_THREADS) gat_segment_sum_kernel(const int32_t* __restrict__ rowptr,
-                                                                      const int32_t* __restrict__ eidx, const float* __restrict__ vals,
-                                                                      int H, int64_t n_rows, float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t j = (int64_t)blockIdx.x * GAT_WARPS + (threadIdx.x >> 5); j < n_rows; j += (int64_t)gridDim.x * GAT_WARPS) {
-    const int b = rowptr[j], e = rowptr[j + 1];
-    for (int h = 0; h < H; ++h) {
-      float s = 0.f;
-      for (int k = b + lane; k < e; k += 32) s += vals[(size_t)(eidx ? eidx[k] : k) * H + h];
-      s = gsum(s);
-      if (lane == 0) out[(size_t)j * H + h] = s;
+template <typename V, int NJ, int U>
+__global__ void __launch_bounds__(GAT_HUB_THREADS) gat_bwd_hub_kernel(const GatBwd p) {
+  constexpr int W = VecTraits<V>::W;
+  __shared__ float s_S[GAT_HUB_WARPS][GAT_MAXH];
+  __shared__ float s_tot[GAT_MAXH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = p.K / W;
+  const int64_t i = __ldg(p.hub_rows + blockIdx.x);
+  const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
+  const V* G = reinterpret_cast<const V*>(p.dout);
+  const size_t lddv = (size_t)(p.ldd / W);
+  int head[NJ];
+  V g[NJ];
+  float S[GAT_MAXH], dr[GAT_MAXH];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    head[j] = ((lane + 32 * j) * W) / p.D;
+    if (lane + 32 * j < nvec) g[j] = vldg(G + (size_t)i * lddv + lane + 32 * j);
+    else vzero(g[j]);
+  }
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
+  bwd_edges<V, NJ, U>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, g, head, S);
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) s_S[warp][h] = S[h];
+  }
+  __syncthreads();
+  if (threadIdx.x < p.H) {
+    float t = 0.f;
+    for (int w = 0; w < GAT_HUB_WARPS; ++w) t += s_S[w][threadIdx.x];
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) S[h] = h < p.H ? s_tot[h] : 0.f;
+  bwd_phase2(p, i, b, e, threadIdx.x, GAT_HUB_THREADS, S, dr);
+  if (p.der) {
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) { const float t = gsum(dr[h]); if (lane == 0) s_S[warp][h] = t; }
+    __syncthreads();
+    if (threadIdx.x < p.H) {
+      float t = 0.f;
+      for (int w = 0; w < GAT_HUB_WARPS; ++w) t += s_S[w][threadIdx.x];
+      p.der[(size_t)i * p.H + threadIdx.x] = t;
     }
   }
 }
@@ -316,16 +436,59 @@ static inline int rows_grid(int64_t n) {
   return (int)(g < 1 ? 1 : g);
 }
 
-template <typename V>
-static int launch_agg(const GatAgg& p, cudaStream_t st) {
+template <typename V, int NJ, int U>
+static int launch_agg_nj(const GatAgg& p, cudaStream_t st) {
   int rc;
-  gat_aggregate_kernel<V><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
+  gat_aggregate_kernel<V, NJ, U><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
-    gat_aggregate_hub_kernel<V><<<p.n_hub, GAT_THREADS, p.K * sizeof(float), st>>>(p);
+    gat_aggregate_hub_kernel<V, NJ, U><<<p.n_hub, GAT_HUB_THREADS, p.K * sizeof(float), st>>>(p);
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
+}
+
+template <typename V, int NJ, int U>
+static int launch_bwd_nj(const GatBwd& p, cudaStream_t st) {
+  int rc;
+  gat_bwd_rows_kernel<V, NJ, U><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
+  if ((rc = check_launch())) return rc;
+  if (p.n_hub > 0) {
+    gat_bwd_hub_kernel<V, NJ, U><<<p.n_hub, GAT_HUB_THREADS, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}
+
+// vectors per lane -> (NJ, U): keep about 8 row vectors in flight per lane; the narrow vector types only get the
+// two widest shapes (they are the odd-width fallbacks)
+template <typename V>
+static int launch_agg(const GatAgg& p, cudaStream_t st) {
+  constexpr int W = VecTraits<V>::W;
+  const int nj = (p.K / W + 31) / 32;
+  if constexpr (W == 4) {
+    if (nj <= 1) return launch_agg_nj<V, 1, 8>(p, st);
+    if (nj <= 2) return launch_agg_nj<V, 2, 4>(p, st);
+  }
+  if (nj <= 4) return launch_agg_nj<V, 4, 2>(p, st);
+  if constexpr (W == 4) {
+    if (nj <= 8) return launch_agg_nj<V, 8, 1>(p, st);
+  }
+  return launch_agg_nj<V, GAT_MAXJ, 1>(p, st);
+}
+template <typename V>
+static int launch_bwd(const GatBwd& p, cudaStream_t st) {
+  constexpr int W = VecTraits<V>::W;
+  const int nj = (p.K / W + 31) / 32;
+  if constexpr (W == 4) {
+    if (nj <= 1) return launch_bwd_nj<V, 1, 8>(p, st);
+    if (nj <= 2) return launch_bwd_nj<V, 2, 4>(p, st);
+  }
+  if (nj <= 4) return launch_bwd_nj<V, 4, 2>(p, st);
+  if constexpr (W == 4) {
+    if (nj <= 8) return launch_bwd_nj<V, 8, 1>(p, st);
+  }
+  return launch_bwd_nj<V, GAT_MAXJ, 1>(p, st);
 }
 
 }  // namespace b200gnn
@@ -337,8 +500,10 @@ extern "C" int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t
                                             void* stream) {
   if (!rowptr || !el || !a || n_rows < 0 || H <= 0 || H > GAT_MAXH) return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
-  gat_edge_softmax_kernel<<<rows_grid(n_rows), GAT_THREADS, 0, (cudaStream_t)stream>>>(rowptr, col, el, er, (int)H,
-                                                                                      negative_slope, softmax_eps, n_rows, a);
+  GatSoftmax p;
+  p.rowptr = rowptr; p.col = col; p.el = el; p.er = er; p.a = a; p.n_rows = n_rows; p.H = (int32_t)H;
+  p.slope = negative_slope; p.eps = softmax_eps;
+  gat_edge_softmax_kernel<<<rows_grid(n_rows), GAT_THREADS, 0, (cudaStream_t)stream>>>(p);
   return check_launch();
 }
 
@@ -371,41 +536,31 @@ extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* co
                                         int64_t H, int64_t D, float negative_slope, float* dpre, float* der,
                                         const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
                                         const int32_t* hub_rows, int64_t n_hub, void* stream) {
-  if (!rowptr || !a || !ft || !dout || !el || !dpre || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < H * D ||
-      ldd < H * D)
+  const int64_t K = H * D;
+  if (!rowptr || !a || !ft || !dout || !el || !dpre || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < K || ldd < K ||
+      !chunk_rowptr || n_chunks < 0 || n_hub < 0 || (n_hub > 0 && !hub_rows))
     return B200GNN_ERR_BAD_ARG;
-  if (n_rows == 0) return B200GNN_OK;
+  if (n_rows == 0 || n_chunks == 0) return B200GNN_OK;
   GatBwd p;
   p.rowptr = rowptr; p.col = col; p.a = a; p.ft = ft; p.dout = dout; p.el = el; p.er = er; p.dpre = dpre; p.der = der;
-  p.ldf = ldf; p.ldd = ldd; p.n_rows = n_rows; p.H = (int32_t)H; p.D = (int32_t)D; p.K = (int32_t)(H * D);
-  p.slope = negative_slope;
-  p.row_list = nullptr; p.chunk_rowptr = chunk_rowptr; p.n_list = 0; p.n_chunks = (int32_t)n_chunks;
-  p.hub_threshold = hub_threshold;
+  p.chunk_rowptr = chunk_rowptr; p.hub_rows = hub_rows;
+  p.ldf = ldf; p.ldd = ldd; p.n_rows = n_rows; p.n_chunks = (int32_t)n_chunks; p.n_hub = (int32_t)n_hub;
+  p.hub_threshold = hub_threshold; p.H = (int32_t)H; p.D = (int32_t)D; p.K = (int32_t)K; p.slope = negative_slope;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t lph = D / 4;
-  const bool fast = chunk_rowptr && n_chunks > 0 && D % 4 == 0 && (lph & (lph - 1)) == 0 && H * D <= 4 * 32 * GAT_FJ &&
-                    ldf % 4 == 0 && ldd % 4 == 0 && aligned_to(ft, 16) && aligned_to(dout, 16) && (n_hub == 0 || hub_rows) &&
-                    lph <= 32;
-  int rc;
-  if (fast) {
-    gat_bwd_rows_warp_kernel<<<(int)((n_chunks + GAT_WARPS - 1) / GAT_WARPS), GAT_THREADS, 0, st>>>(p);
-    if ((rc = check_launch())) return rc;
-    if (n_hub > 0) {
-      p.row_list = hub_rows; p.n_list = (int32_t)n_hub;
-      gat_bwd_rows_kernel<<<(int)n_hub, GAT_THREADS, 0, st>>>(p);
-      if ((rc = check_launch())) return rc;
-    }
-    return B200GNN_OK;
-  }
-  int64_t grid = n_rows < 148 * 32 ? n_rows : 148 * 32;
-  gat_bwd_rows_kernel<<<(int)grid, GAT_THREADS, 0, st>>>(p);
-  return check_launch();
+  if (D % 4 == 0 && ldf % 4 == 0 && ldd % 4 == 0 && aligned_to(ft, 16) && aligned_to(dout, 16) && K <= 4 * 32 * GAT_MAXJ)
+    return launch_bwd<float4>(p, st);
+  if (D % 2 == 0 && ldf % 2 == 0 && ldd % 2 == 0 && aligned_to(ft, 8) && aligned_to(dout, 8) && K <= 2 * 32 * GAT_MAXJ)
+    return launch_bwd<float2>(p, st);
+  if (K <= 32 * GAT_MAXJ) return launch_bwd<float>(p, st);
+  return B200GNN_ERR_UNSUPPORTED;
 }
 
 extern "C" int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx, const float* vals, int64_t n_rows,
                                              int64_t H, float* out, void* stream) {
-  if (!rowptr || !vals || !out || n_rows < 0 || H <= 0) return B200GNN_ERR_BAD_ARG;
+  if (!rowptr || !vals || !out || n_rows < 0 || H <= 0 || H > GAT_MAXH) return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
-  gat_segment_sum_kernel<<<rows_grid(n_rows), GAT_THREADS, 0, (cudaStream_t)stream>>>(rowptr, eidx, vals, (int)H, n_rows, out);
+  GatSegSum p;
+  p.rowptr = rowptr; p.eidx = eidx; p.vals = vals; p.out = out; p.n_rows = n_rows; p.H = (int32_t)H;
+  gat_segment_sum_kernel<<<rows_grid(n_rows), GAT_THREADS, 0, (cudaStream_t)stream>>>(p);
   return check_launch();
 }

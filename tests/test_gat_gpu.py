@@ -24,7 +24,8 @@ def graph(n, e, seed, self_loops=True):
 
 
 @pytest.mark.parametrize("H,D,with_er,eps", [(8, 32, True, 0.0), (3, 250, False, 0.0), (4, 16, True, 1e-16), (1, 7, True, 0.0),
-                                             (6, 10, True, 0.0)])
+                                             (6, 10, True, 0.0), (4, 100, True, 0.0), (4, 200, False, 0.0),
+                                             (16, 80, True, 0.0), (3, 101, True, 0.0), (3, 40, True, 0.0)])
 def test_gat_aggregate_forward_backward(H, D, with_er, eps):
     n = 4000
     r, c = graph(n, 30_000, H + D)          # skewed: contains hub rows above the split threshold
