@@ -273,13 +273,20 @@ struct GatBwd {
 };
 
 // phase 1 over a group's share of the row's edges: d a[k,h] = <ft[src,h,:], dout[i,h,:]> staged in dpre, and the
-// group-local S[h] += a[k,h] * d a[k,h] (same value on every lane).
-template <typename V, int NJ, int U>
+// group-local S[h] += a[k,h] * d a[k,h] (same value on every lane).  Per-head sums over the lanes: SEG = false
+// reduces one head at a time over the whole warp (H * 5 shuffles per edge; right for few wide heads, e.g. the
+// teacher's 3 x 250); SEG = true needs D/W a power of two <= 32, so a head is an aligned group of lph lanes of one
+// vector index j, and a segmented xor-reduction costs NJ * log2(lph) shuffles (many narrow heads).
+template <typename V, int NJ, int U, bool SEG>
 __device__ __forceinline__ void bwd_edges(const GatBwd& p, int beg, int end, int first, int stride, int lane, int nvec,
                                           const V (&g)[NJ], const int (&head)[NJ], float (&S)[GAT_MAXH]) {
   constexpr int W = VecTraits<V>::W;
   const V* F = reinterpret_cast<const V*>(p.ft);
   const size_t ldv = (size_t)(p.ldf / W);
+  const int lph = p.D / W;
+  float Sj[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) Sj[j] = 0.f;
   for (int k0 = beg + first * U; k0 < end; k0 += stride * U) {
     V x[U][NJ];
 #pragma unroll
@@ -304,19 +311,44 @@ __device__ __forceinline__ void bwd_edges(const GatBwd& p, int beg, int end, int
         float d[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) d[j] = vdot(x[u][j], g[j]);
+        if (SEG) {
 #pragma unroll
-        for (int h = 0; h < GAT_MAXH; ++h)
-          if (h < p.H) {
-            float part = 0.f;
+          for (int j = 0; j < NJ; ++j) {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) part += (head[j] == h) ? d[j] : 0.f;
-            const float da = gsum(part);
-            const size_t o = (size_t)kk * p.H + h;
-            if (lane == 0) p.dpre[o] = da;
-            S[h] = fmaf(__ldg(p.a + o), da, S[h]);
+            for (int o = 1; o < 32; o <<= 1)
+              if (o < lph) d[j] += __shfl_xor_sync(FULL_MASK, d[j], o);
+            if (lane + 32 * j < nvec) {
+              const size_t o = (size_t)kk * p.H + head[j];
+              if ((lane & (lph - 1)) == 0) p.dpre[o] = d[j];
+              Sj[j] = fmaf(__ldg(p.a + o), d[j], Sj[j]);
+            }
           }
+        } else {
+#pragma unroll
+          for (int h = 0; h < GAT_MAXH; ++h)
+            if (h < p.H) {
+              float part = 0.f;
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) part += (head[j] == h) ? d[j] : 0.f;
+              const float da = gsum(part);
+              const size_t o = (size_t)kk * p.H + h;
+              if (lane == 0) p.dpre[o] = da;
+              S[h] = fmaf(__ldg(p.a + o), da, S[h]);
+            }
+        }
       }
     }
+  }
+  if (SEG) {   // head h lives in vector index v = h*lph: lane v%32 of j = v/32 holds its S
+#pragma unroll
+    for (int h = 0; h < GAT_MAXH; ++h)
+      if (h < p.H) {
+        const int v = h * lph;
+        float val = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) val = (j == (v >> 5)) ? Sj[j] : val;
+        S[h] = __shfl_sync(FULL_MASK, val, v & 31);
+      }
   }
 }
 
@@ -343,7 +375,7 @@ __device__ __forceinline__ void bwd_phase2(const GatBwd& p, int64_t i, int b, in
   }
 }
 
-template <typename V, int NJ, int U>
+template <typename V, int NJ, int U, bool SEG>
 __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd p) {
   constexpr int W = VecTraits<V>::W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -368,7 +400,7 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd 
     }
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
-    bwd_edges<V, NJ, U>(p, b, e, 0, 1, lane, nvec, g, head, S);
+    bwd_edges<V, NJ, U, SEG>(p, b, e, 0, 1, lane, nvec, g, head, S);
     __syncwarp();                                   // lane 0's staged d a is read by every lane below
     bwd_phase2(p, i, b, e, lane, 32, S, dr);
     if (p.der) {
@@ -379,7 +411,7 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd 
   }
 }
 
-template <typename V, int NJ, int U>
+template <typename V, int NJ, int U, bool SEG>
 __global__ void __launch_bounds__(GAT_HUB_THREADS) gat_bwd_hub_kernel(const GatBwd p) {
   constexpr int W = VecTraits<V>::W;
   __shared__ float s_S[GAT_HUB_WARPS][GAT_MAXH];
@@ -401,7 +433,7 @@ __global__ void __launch_bounds__(GAT_HUB_THREADS) gat_bwd_hub_kernel(const GatB
   }
 #pragma unroll
   for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
-  bwd_edges<V, NJ, U>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, g, head, S);
+  bwd_edges<V, NJ, U, SEG>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, g, head, S);
   if (lane == 0) {
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h)
@@ -448,16 +480,27 @@ static int launch_agg_nj(const GatAgg& p, cudaStream_t st) {
   return B200GNN_OK;
 }
 
-template <typename V, int NJ, int U>
-static int launch_bwd_nj(const GatBwd& p, cudaStream_t st) {
+template <typename V, int NJ, int U, bool SEG>
+static int launch_bwd_seg(const GatBwd& p, cudaStream_t st) {
   int rc;
-  gat_bwd_rows_kernel<V, NJ, U><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
+  gat_bwd_rows_kernel<V, NJ, U, SEG><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
-    gat_bwd_hub_kernel<V, NJ, U><<<p.n_hub, GAT_HUB_THREADS, 0, st>>>(p);
+    gat_bwd_hub_kernel<V, NJ, U, SEG><<<p.n_hub, GAT_HUB_THREADS, 0, st>>>(p);
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
+}
+template <typename V, int NJ, int U>
+static int launch_bwd_nj(const GatBwd& p, cudaStream_t st) {
+  constexpr int W = VecTraits<V>::W;
+  if constexpr (W == 4) {   // segmented reduction when it is cheaper than H whole-warp sums
+    const int lph = p.D / W, nj = (p.K / W + 31) / 32;
+    int lg = 0;
+    while ((1 << lg) < lph) ++lg;
+    if (lph <= 32 && (lph & (lph - 1)) == 0 && nj * lg < p.H * 5) return launch_bwd_seg<V, NJ, U, true>(p, st);
+  }
+  return launch_bwd_seg<V, NJ, U, false>(p, st);
 }
 
 // vectors per lane -> (NJ, U): keep about 8 row vectors in flight per lane; the narrow vector types only get the
