@@ -142,6 +142,62 @@ class SAGEConv(torch.nn.Module):
         return f"SAGEConv({self.in_channels}, {self.out_channels})"
 
 
+class DGLGraphConv(torch.nn.Module):
+    """DGL ``GraphConv(in, out, norm='both')`` as the reference's DGL student uses it (arxiv_dgl/models.py:46-92, ctor :65):
+    ``out = D_in^-1/2 A D_out^-1/2 x W + b`` with degrees clamped to >= 1 and no self-loops added (the script adds them to the
+    graph).  Called as ``conv(adj_t, feat)`` with a SparseTensor (row = destination, col = source) in place of the DGL graph.
+    The two degree scalings are folded into the edge values once per adjacency, so the layer is one weighted SpMM and one
+    tcgen05 GEMM; like DGL the narrower side is aggregated (W first iff in > out)."""
+
+    def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None):
+        super().__init__()
+        if norm != "both" or not weight:
+            raise NotImplementedError("the reference only uses GraphConv(norm='both') with a weight")
+        self._in, self._out, self._activation = in_feats, out_feats, activation
+        self.weight = torch.nn.Parameter(torch.empty(in_feats, out_feats))
+        self.bias = torch.nn.Parameter(torch.empty(out_feats)) if bias else None
+        self._norm_adj = (None, None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            torch.nn.init.zeros_(self.bias)
+
+    def _normalised(self, adj_t: SparseTensor) -> SparseTensor:
+        if self._norm_adj[0] is not adj_t:
+            st = adj_t.storage
+            row, col = st.row(), st.col()
+            d_in = st.rowcount().clamp(min=1).to(torch.float32).pow(-0.5)
+            d_out = torch.bincount(col, minlength=adj_t.size(1)).clamp(min=1).to(torch.float32).pow(-0.5)
+            val = d_in[row] * d_out[col]
+            if st.value() is not None:
+                val = val * st.value()
+            self._norm_adj = (adj_t, adj_t.set_value(val, layout="coo"))
+        return self._norm_adj[1]
+
+    def forward(self, adj_t: SparseTensor, feat: torch.Tensor) -> torch.Tensor:
+        A = self._normalised(adj_t)
+        if self._in > self._out:
+            rst = ops.matmul(A, linear(feat, self.weight.t()), "add")
+        else:
+            rst = linear(ops.matmul(A, feat, "add"), self.weight.t())
+        if self.bias is not None:
+            rst = rst + self.bias
+        return rst if self._activation is None else self._activation(rst)
+
+
+def neighbor_average_features(adj_t: SparseTensor, feat: torch.Tensor, R: int):
+    """SIGN precompute (arxiv_dgl/sign.py:175-183): ``feat_r = mean over in-neighbours of feat_{r-1}`` for r = 1..R
+    (DGL ``update_all(copy_u, mean)``; nodes without in-edges get zeros).  Returns ``[feat_0, ..., feat_R]`` —
+    R chained mean-SpMMs on the same CSR plan."""
+    A = adj_t.set_value(None) if adj_t.has_value() else adj_t
+    res = [feat]
+    for _ in range(R):
+        res.append(ops.matmul(A, res[-1], "mean"))
+    return res
+
+
 # ----------------------------------------------------------------------------------------- generic message passing
 def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = 0, dim_size: Optional[int] = None, reduce: str = "sum"):
     """torch_scatter.scatter(src, index, dim=0, dim_size, reduce in {sum, add, mean}) as one SpMM: the [dim_size x E]

@@ -90,3 +90,34 @@ def gat_aggregate(ft, el, er, row, col, n_dst: int, heads: int, negative_slope: 
     msg = ft.index_select(0, col).view(-1, H, D) * a.unsqueeze(-1)
     out = torch.zeros(n_dst, H, D, dtype=ft.dtype).index_add_(0, row, msg)
     return out.reshape(n_dst, H * D)
+
+
+def dgl_graph_conv_both(x, row, col, n: int, weight, bias=None):
+    """DGL GraphConv(norm='both') as called at arxiv_dgl/models.py:65,80 (DGL 0.5/0.6 semantics restated: scale sources by
+    out_degree^-1/2 (degrees clamped to >= 1), multiply by W first iff in > out, sum over in-edges, scale by in_degree^-1/2,
+    add bias).  row = destination, col = source of each edge."""
+    d_out = torch.bincount(col, minlength=n).clamp(min=1).to(x.dtype).pow(-0.5)
+    d_in = torch.bincount(row, minlength=n).clamp(min=1).to(x.dtype).pow(-0.5)
+    h = x * d_out[:, None]
+    if weight.shape[0] > weight.shape[1]:
+        h = h @ weight
+        rst = ops.scatter(h[col], row, n, "sum")
+    else:
+        rst = ops.scatter(h[col], row, n, "sum") @ weight
+    rst = rst * d_in[:, None]
+    return rst if bias is None else rst + bias
+
+
+def neighbor_average_features(x, row, col, n: int, R: int):
+    """arxiv_dgl/sign.py:175-183: R rounds of update_all(copy_u, mean) — mean over in-edges, zero where there are none."""
+    res = [x]
+    for _ in range(R):
+        res.append(ops.scatter(res[-1][col], row, n, "mean"))
+    return res
+
+
+def projection_gcd(x, rowptr, col, val, lin_w, lin_b, conv_w, conv_b, gamma, beta):
+    """ProjectionGCD.forward (arxiv_pyg/gnn.py:95-99): relu(BN(Linear(x) + GCNConv(x, adj_t))); rowptr/col/val is the
+    gcn-normalised adjacency (the reference's conv is non-cached, i.e. it re-derives the same normalisation every call)."""
+    h = F.linear(x, lin_w, lin_b) + gcn_conv(x, rowptr, col, val, conv_w, conv_b)
+    return torch.relu(batch_norm_train(h, gamma, beta))

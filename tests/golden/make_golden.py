@@ -177,6 +177,17 @@ def main():
                             grads={k: p.grad.detach().clone() for k, p in m.named_parameters()})
         m.eval()
         models[name]["logits_eval"] = m(x, adj).detach()
+    # ---- the reference's ProjectionGCD head (gnn.py:88-99): relu(BN(Linear(x) + GCNConv(x, adj_t))), non-cached conv
+    torch.manual_seed(2)
+    pg = gnn.ProjectionGCD(16, 12)
+    pg.train()
+    xin = x.clone().requires_grad_(True)
+    wout = torch.randn(n, 12, generator=g)
+    pout = pg(xin, adj)
+    (pout * wout).sum().backward()
+    models["proj_gcd"] = dict(state={k: v.detach().clone() for k, v in pg.state_dict().items()}, out_train=pout.detach(),
+                              w=wout, d_x=xin.grad.detach().clone(),
+                              grads={k: p.grad.detach().clone() for k, p in pg.named_parameters()})
     torch.save(dict(edge_index_directed=torch.from_numpy(ei), sym_row=torch.from_numpy(r), sym_col=torch.from_numpy(c),
                     x=x, train_idx=train_idx, sub_edge_index=sub_ei, models=models), OUT / "model_arxiv.pt")
     print("wrote", [p.name for p in OUT.glob("*.pt")])

@@ -153,3 +153,37 @@ def test_oracle_sage_reproduces_reference_model_fixture(golden_model):
     logits, hidden = onn.sage_forward(G["x"], ptr, c, P, ga, be, None)
     assert rel_err(logits, m["logits_train"]) < 1e-5
     assert rel_err(hidden, m["out_feat"]) < 1e-5
+
+
+def test_oracle_projection_gcd_reproduces_reference_fixture(golden_model):
+    G, m = golden_model, golden_model["models"]["proj_gcd"]
+    n = G["x"].shape[0]
+    r, c, v = og.gcn_norm(G["sym_row"].numpy(), G["sym_col"].numpy(), n)
+    ptr, c, v = torch.from_numpy(og.ind2ptr(r, n)), torch.from_numpy(c), torch.from_numpy(v)
+    st = {k: t.clone().requires_grad_(t.is_floating_point()) for k, t in m["state"].items()}
+    x = G["x"].clone().requires_grad_(True)
+    out = onn.projection_gcd(x, ptr, c, v, st["lin.weight"], st["lin.bias"], st["conv.weight"], st["conv.bias"],
+                             st["bn.weight"], st["bn.bias"])
+    assert rel_err(out, m["out_train"]) < 1e-5
+    (out * m["w"]).sum().backward()
+    assert rel_err(x.grad, m["d_x"]) < 5e-5
+    for k in ("lin.weight", "conv.weight", "bn.weight", "bn.bias"):
+        assert rel_err(st[k].grad, m["grads"][k]) < 5e-5, k
+
+
+def test_dgl_graph_conv_and_sign_average_against_dense():
+    """oracle.nn.dgl_graph_conv_both / neighbor_average_features vs an explicit dense adjacency."""
+    from oracle import nn as onn
+    g = torch.Generator().manual_seed(5)
+    n, e = 60, 400
+    row, col = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    A = torch.zeros(n, n, dtype=torch.float64).index_put_((row, col), torch.ones(e, dtype=torch.float64), accumulate=True)
+    x = torch.randn(n, 7, generator=g, dtype=torch.float64)
+    for fout in (3, 9):
+        W = torch.randn(7, fout, generator=g, dtype=torch.float64)
+        din, dout = A.sum(1).clamp(min=1).pow(-0.5), A.sum(0).clamp(min=1).pow(-0.5)
+        want = (din[:, None] * (A @ (dout[:, None] * x))) @ W
+        assert torch.allclose(onn.dgl_graph_conv_both(x, row, col, n, W), want, atol=1e-12)
+    hops = onn.neighbor_average_features(x, row, col, n, 2)
+    M = A / A.sum(1).clamp(min=1)[:, None]
+    assert torch.allclose(hops[2], M @ (M @ x), atol=1e-12)

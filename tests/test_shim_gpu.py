@@ -59,6 +59,37 @@ def test_module_path_reproduces_reference_fixture(golden_model, name, cls, kw):
     assert rel_err(model(G["x"].cuda(), adj), m["logits_eval"]) < 1e-5
 
 
+class ProjectionGCD(torch.nn.Module):
+    """Same module tree as the reference's ProjectionGCD (arxiv_pyg/gnn.py:88-99) on the mirrored layers."""
+
+    def __init__(self, hidden, proj):
+        super().__init__()
+        self.lin = bnn.Linear(hidden, proj)
+        self.conv = bnn.GCNConv(hidden, proj)          # non-cached: normalises the adjacency on every call
+        self.bn = torch.nn.BatchNorm1d(proj)
+
+    def forward(self, x, adj_t):
+        return F.relu(self.bn(self.lin(x) + self.conv(x, adj_t)))
+
+
+def test_projection_gcd_reproduces_reference_fixture(golden_model):
+    G, m = golden_model, golden_model["models"]["proj_gcd"]
+    n = G["x"].shape[0]
+    adj = SparseTensor(row=G["sym_row"].cuda(), col=G["sym_col"].cuda(), sparse_sizes=(n, n), is_sorted=True)
+    head = ProjectionGCD(16, 12).cuda()
+    head.load_state_dict(m["state"])
+    head.train()
+    x = G["x"].cuda().requires_grad_(True)
+    out = head(x, adj)
+    assert rel_err(out, m["out_train"]) < 1e-5
+    (out * m["w"].cuda()).sum().backward()
+    assert rel_err(x.grad, m["d_x"]) < 5e-5
+    for k, p in head.named_parameters():
+        if k in ("lin.bias", "conv.bias"):
+            continue                                   # zero-gradient biases in front of BatchNorm
+        assert rel_err(p.grad, m["grads"][k]) < 5e-5, k
+
+
 def test_message_passing_mean_matches_oracle_scatter():
     class Rel(bnn.MessagePassing):
         def __init__(self):
