@@ -8,8 +8,10 @@
 //           d er, d pre[nnz,H]) + gat_segment_sum (d el over the transposed graph).
 // Work split.  Row-wide kernels (aggregate, bwd_rows): one warp per chunk of rows (the SpMM chunk plan); lanes own
 // vectors lane+32j of the K-float row and U edges are loaded before they are consumed, so U*NJ independent row
-// gathers are in flight per warp.  Rows above hub_threshold go to one 512-thread CTA each (16 warps stride over
-// groups of U edges, partials combined in warp order through shared memory).  Scalar kernels (edge softmax,
+// gathers are in flight per warp.  Rows above hub_threshold are split into seg_len-edge segments (the SpMM hub plan):
+// one CTA per segment, scheduled as the first CTAs of the same launch, 8 warps striding over groups of U edges and
+// combining in warp order through shared memory into a per-segment partial; a small finalize kernel adds a hub
+// row's segments in order (and, in the backward, runs the softmax pass once S is complete).  Scalar kernels (edge softmax,
 // segment sum): lanes stride over a row's edges and carry all H heads at once; rows above GAT_CTA_DEG are taken
 // by the whole CTA.  No atomics anywhere: every sum has a fixed order.
 #include "common.cuh"
@@ -17,7 +19,6 @@
 namespace b200gnn {
 
 constexpr int GAT_THREADS = 256, GAT_WARPS = 8, GAT_MAXH = 16, GAT_MAXJ = 12;
-constexpr int GAT_HUB_THREADS = 512, GAT_HUB_WARPS = 16;
 constexpr int GAT_CTA_DEG = 512;
 
 __device__ __forceinline__ float gsum(float v) {
@@ -165,11 +166,24 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_segment_sum_kernel(const GatS
 // ---------------------------------------------------------------- aggregate
 struct GatAgg {
   const int32_t* rowptr; const int32_t* col; const int32_t* eidx;   // eidx: position of edge k in a[] (NULL: k)
-  const int32_t* chunk_rowptr; const int32_t* hub_rows;
-  const float* a; const float* ft; float* out;
+  const int32_t* chunk_rowptr; const int32_t* hub_rows; const int32_t* hub_segptr;
+  const float* a; const float* ft; float* out; float* ws;   // ws: [n_seg, K] hub-segment partials
   int64_t ldf, ldo;
-  int32_t n_chunks, n_hub, hub_threshold, H, D, K;
+  int32_t n_chunks, n_hub, n_seg, seg_len, hub_threshold, H, D, K;
 };
+
+// segment s of the hub plan -> (hub index, edge range)
+__device__ __forceinline__ void hub_segment(const int32_t* rowptr, const int32_t* hub_rows, const int32_t* hub_segptr,
+                                            int n_hub, int seg_len, int s, int& r, int& b, int& e) {
+  int lo = 0, hi = n_hub;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(hub_segptr + mid) <= s) lo = mid; else hi = mid;
+  }
+  r = __ldg(hub_rows + lo);
+  b = __ldg(rowptr + r) + (s - __ldg(hub_segptr + lo)) * seg_len;
+  e = min(__ldg(rowptr + r + 1), b + seg_len);
+}
 
 // lane handles vectors v = lane + 32*j (j < NJ) of width W; head of vector v = (v*W)/D.  The group's warps take
 // groups of U consecutive edges: warp `first` of `stride` warps starts at beg + first*U.
@@ -208,15 +222,37 @@ __device__ __forceinline__ void agg_edges(const GatAgg& p, int beg, int end, int
 template <typename V, int NJ, int U>
 __global__ void __launch_bounds__(GAT_THREADS) gat_aggregate_kernel(const GatAgg p) {
   constexpr int W = VecTraits<V>::W;
+  extern __shared__ float s_row[];   // K floats (hub-segment CTAs)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = p.K / W;
-  V* O = reinterpret_cast<V*>(p.out);
-  const size_t ldov = (size_t)(p.ldo / W);
-  const int chunk = blockIdx.x * GAT_WARPS + warp;
-  if (chunk >= p.n_chunks) return;
   int head[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) head[j] = ((lane + 32 * j) * W) / p.D;
+  if ((int)blockIdx.x < p.n_seg) {     // hub segment: warps stride over groups of U edges, combined in warp order
+    int r, b, e;
+    hub_segment(p.rowptr, p.hub_rows, p.hub_segptr, p.n_hub, p.seg_len, blockIdx.x, r, b, e);
+    V acc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) vzero(acc[j]);
+    agg_edges<V, NJ, U>(p, b, e, warp, GAT_WARPS, lane, nvec, head, acc);
+    for (int i = threadIdx.x; i < p.K; i += GAT_THREADS) s_row[i] = 0.f;
+    __syncthreads();
+    V* sv = reinterpret_cast<V*>(s_row);
+    for (int w = 0; w < GAT_WARPS; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (lane + 32 * j < nvec) { V t = sv[lane + 32 * j]; vadd(t, acc[j]); sv[lane + 32 * j] = t; }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < p.K; i += GAT_THREADS) p.ws[(size_t)blockIdx.x * p.K + i] = s_row[i];
+    return;
+  }
+  V* O = reinterpret_cast<V*>(p.out);
+  const size_t ldov = (size_t)(p.ldo / W);
+  const int chunk = (blockIdx.x - p.n_seg) * GAT_WARPS + warp;
+  if (chunk >= p.n_chunks) return;
   const int r0 = __ldg(p.chunk_rowptr + chunk), r1 = __ldg(p.chunk_rowptr + chunk + 1);
   for (int r = r0; r < r1; ++r) {
     const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
@@ -231,32 +267,18 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_aggregate_kernel(const GatAgg
   }
 }
 
-// one CTA per hub row: warps stride over groups of U edges, partials combined in warp order through shared memory
-template <typename V, int NJ, int U>
-__global__ void __launch_bounds__(GAT_HUB_THREADS) gat_aggregate_hub_kernel(const GatAgg p) {
-  constexpr int W = VecTraits<V>::W;
-  extern __shared__ float s_row[];   // K floats
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = p.K / W;
-  const int r = __ldg(p.hub_rows + blockIdx.x);
-  const int b = __ldg(p.rowptr + r), e = __ldg(p.rowptr + r + 1);
-  int head[NJ];
-  V acc[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) { head[j] = ((lane + 32 * j) * W) / p.D; vzero(acc[j]); }
-  agg_edges<V, NJ, U>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, head, acc);
-  for (int i = threadIdx.x; i < p.K; i += GAT_HUB_THREADS) s_row[i] = 0.f;
-  __syncthreads();
-  V* sv = reinterpret_cast<V*>(s_row);
-  for (int w = 0; w < GAT_HUB_WARPS; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (lane + 32 * j < nvec) { V t = sv[lane + 32 * j]; vadd(t, acc[j]); sv[lane + 32 * j] = t; }
-    }
-    __syncthreads();
+// out[hub row] = its segments' partials added in segment order
+__global__ void __launch_bounds__(GAT_THREADS) gat_hub_finalize_kernel(const int32_t* __restrict__ hub_rows,
+                                                                       const int32_t* __restrict__ hub_segptr,
+                                                                       const float* __restrict__ ws, float* __restrict__ out,
+                                                                       int64_t ldo, int K) {
+  const int r = __ldg(hub_rows + blockIdx.x);
+  const int q0 = __ldg(hub_segptr + blockIdx.x), q1 = __ldg(hub_segptr + blockIdx.x + 1);
+  for (int i = threadIdx.x; i < K; i += GAT_THREADS) {
+    float t = 0.f;
+    for (int q = q0; q < q1; ++q) t += ws[(size_t)q * K + i];
+    out[(size_t)r * ldo + i] = t;
   }
-  for (int i = threadIdx.x; i < p.K; i += GAT_HUB_THREADS) p.out[(size_t)r * p.ldo + i] = s_row[i];
 }
 
 // ---------------------------------------------------------------- backward, per destination row
@@ -265,9 +287,10 @@ struct GatBwd {
   const float* el; const float* er;
   float* dpre;   // [nnz,H]  out: d loss / d (el[src]+er[dst])
   float* der;    // [n_rows,H] out (may be NULL when there is no er)
-  const int32_t* chunk_rowptr; const int32_t* hub_rows;
+  const int32_t* chunk_rowptr; const int32_t* hub_rows; const int32_t* hub_segptr;
+  float* ws;     // [n_seg, H] hub-segment partials of S
   int64_t ldf, ldd, n_rows;
-  int32_t n_chunks, n_hub, hub_threshold;
+  int32_t n_chunks, n_hub, n_seg, seg_len, hub_threshold;
   int32_t H, D, K;
   float slope;
 };
@@ -378,21 +401,46 @@ __device__ __forceinline__ void bwd_phase2(const GatBwd& p, int64_t i, int b, in
 template <typename V, int NJ, int U, bool SEG>
 __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd p) {
   constexpr int W = VecTraits<V>::W;
+  __shared__ float s_S[GAT_WARPS][GAT_MAXH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * GAT_WARPS + warp;
-  if (chunk >= p.n_chunks) return;
   const int nvec = p.K / W;
   const V* G = reinterpret_cast<const V*>(p.dout);
   const size_t lddv = (size_t)(p.ldd / W);
   int head[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) head[j] = ((lane + 32 * j) * W) / p.D;
+  V g[NJ];
+  float S[GAT_MAXH], dr[GAT_MAXH];
+#pragma unroll
+  for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
+  if ((int)blockIdx.x < p.n_seg) {     // hub segment: phase 1 only, partial S to the workspace
+    int i, b, e;
+    hub_segment(p.rowptr, p.hub_rows, p.hub_segptr, p.n_hub, p.seg_len, blockIdx.x, i, b, e);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (lane + 32 * j < nvec) g[j] = vldg(G + (size_t)i * lddv + lane + 32 * j);
+      else vzero(g[j]);
+    }
+    bwd_edges<V, NJ, U, SEG>(p, b, e, warp, GAT_WARPS, lane, nvec, g, head, S);
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < GAT_MAXH; ++h)
+        if (h < p.H) s_S[warp][h] = S[h];
+    }
+    __syncthreads();
+    if (threadIdx.x < p.H) {
+      float t = 0.f;
+      for (int w = 0; w < GAT_WARPS; ++w) t += s_S[w][threadIdx.x];
+      p.ws[(size_t)blockIdx.x * p.H + threadIdx.x] = t;
+    }
+    return;
+  }
+  const int chunk = (blockIdx.x - p.n_seg) * GAT_WARPS + warp;
+  if (chunk >= p.n_chunks) return;
   const int r0 = __ldg(p.chunk_rowptr + chunk), r1 = __ldg(p.chunk_rowptr + chunk + 1);
   for (int i = r0; i < r1; ++i) {
     const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
     if (e - b > p.hub_threshold) continue;
-    V g[NJ];
-    float S[GAT_MAXH], dr[GAT_MAXH];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       if (lane + 32 * j < nvec) g[j] = vldg(G + (size_t)i * lddv + lane + 32 * j);
@@ -411,44 +459,24 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_bwd_rows_kernel(const GatBwd 
   }
 }
 
-template <typename V, int NJ, int U, bool SEG>
-__global__ void __launch_bounds__(GAT_HUB_THREADS) gat_bwd_hub_kernel(const GatBwd p) {
-  constexpr int W = VecTraits<V>::W;
-  __shared__ float s_S[GAT_HUB_WARPS][GAT_MAXH];
+// hub rows, after their segments: S = sum of the segment partials (segment order), then phase 2 over the whole row
+__global__ void __launch_bounds__(GAT_THREADS) gat_bwd_hub_finalize_kernel(const GatBwd p) {
+  __shared__ float s_S[GAT_WARPS][GAT_MAXH];
   __shared__ float s_tot[GAT_MAXH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = p.K / W;
   const int64_t i = __ldg(p.hub_rows + blockIdx.x);
   const int b = __ldg(p.rowptr + i), e = __ldg(p.rowptr + i + 1);
-  const V* G = reinterpret_cast<const V*>(p.dout);
-  const size_t lddv = (size_t)(p.ldd / W);
-  int head[NJ];
-  V g[NJ];
-  float S[GAT_MAXH], dr[GAT_MAXH];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    head[j] = ((lane + 32 * j) * W) / p.D;
-    if (lane + 32 * j < nvec) g[j] = vldg(G + (size_t)i * lddv + lane + 32 * j);
-    else vzero(g[j]);
-  }
-#pragma unroll
-  for (int h = 0; h < GAT_MAXH; ++h) S[h] = 0.f;
-  bwd_edges<V, NJ, U, SEG>(p, b, e, warp, GAT_HUB_WARPS, lane, nvec, g, head, S);
-  if (lane == 0) {
-#pragma unroll
-    for (int h = 0; h < GAT_MAXH; ++h)
-      if (h < p.H) s_S[warp][h] = S[h];
-  }
-  __syncthreads();
   if (threadIdx.x < p.H) {
     float t = 0.f;
-    for (int w = 0; w < GAT_HUB_WARPS; ++w) t += s_S[w][threadIdx.x];
+    for (int q = __ldg(p.hub_segptr + blockIdx.x); q < __ldg(p.hub_segptr + blockIdx.x + 1); ++q)
+      t += p.ws[(size_t)q * p.H + threadIdx.x];
     s_tot[threadIdx.x] = t;
   }
   __syncthreads();
+  float S[GAT_MAXH], dr[GAT_MAXH];
 #pragma unroll
   for (int h = 0; h < GAT_MAXH; ++h) S[h] = h < p.H ? s_tot[h] : 0.f;
-  bwd_phase2(p, i, b, e, threadIdx.x, GAT_HUB_THREADS, S, dr);
+  bwd_phase2(p, i, b, e, threadIdx.x, GAT_THREADS, S, dr);
   if (p.der) {
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h)
@@ -456,7 +484,7 @@ __global__ void __launch_bounds__(GAT_HUB_THREADS) gat_bwd_hub_kernel(const GatB
     __syncthreads();
     if (threadIdx.x < p.H) {
       float t = 0.f;
-      for (int w = 0; w < GAT_HUB_WARPS; ++w) t += s_S[w][threadIdx.x];
+      for (int w = 0; w < GAT_WARPS; ++w) t += s_S[w][threadIdx.x];
       p.der[(size_t)i * p.H + threadIdx.x] = t;
     }
   }
@@ -471,10 +499,11 @@ static inline int rows_grid(int64_t n) {
 template <typename V, int NJ, int U>
 static int launch_agg_nj(const GatAgg& p, cudaStream_t st) {
   int rc;
-  gat_aggregate_kernel<V, NJ, U><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
+  const int grid = p.n_seg + (p.n_chunks + GAT_WARPS - 1) / GAT_WARPS;
+  gat_aggregate_kernel<V, NJ, U><<<grid, GAT_THREADS, p.n_seg > 0 ? p.K * sizeof(float) : 0, st>>>(p);
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
-    gat_aggregate_hub_kernel<V, NJ, U><<<p.n_hub, GAT_HUB_THREADS, p.K * sizeof(float), st>>>(p);
+    gat_hub_finalize_kernel<<<p.n_hub, GAT_THREADS, 0, st>>>(p.hub_rows, p.hub_segptr, p.ws, p.out, p.ldo, p.K);
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
@@ -483,10 +512,11 @@ static int launch_agg_nj(const GatAgg& p, cudaStream_t st) {
 template <typename V, int NJ, int U, bool SEG>
 static int launch_bwd_seg(const GatBwd& p, cudaStream_t st) {
   int rc;
-  gat_bwd_rows_kernel<V, NJ, U, SEG><<<(p.n_chunks + GAT_WARPS - 1) / GAT_WARPS, GAT_THREADS, 0, st>>>(p);
+  const int grid = p.n_seg + (p.n_chunks + GAT_WARPS - 1) / GAT_WARPS;
+  gat_bwd_rows_kernel<V, NJ, U, SEG><<<grid, GAT_THREADS, 0, st>>>(p);
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
-    gat_bwd_hub_kernel<V, NJ, U, SEG><<<p.n_hub, GAT_HUB_THREADS, 0, st>>>(p);
+    gat_bwd_hub_finalize_kernel<<<p.n_hub, GAT_THREADS, 0, st>>>(p);
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
@@ -553,16 +583,20 @@ extern "C" int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t
 extern "C" int b200gnn_gat_aggregate_f32(const int32_t* rowptr, const int32_t* col, const int32_t* eidx, const float* a,
                                          const float* ft, int64_t ldf, float* out, int64_t ldo, int64_t n_rows, int64_t H,
                                          int64_t D, const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
-                                         const int32_t* hub_rows, int64_t n_hub, void* stream) {
+                                         int32_t seg_len, const int32_t* hub_rows, const int32_t* hub_segptr, int64_t n_hub,
+                                         int64_t n_seg, float* hub_workspace, void* stream) {
   const int64_t K = H * D;
   if (!rowptr || !a || !ft || !out || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < K || ldo < K || !chunk_rowptr ||
-      n_chunks < 0 || n_hub < 0 || (n_hub > 0 && !hub_rows))
+      n_chunks < 0 || n_hub < 0 || n_seg < n_hub ||
+      (n_hub > 0 && (!hub_rows || !hub_segptr || !hub_workspace || seg_len <= 0)))
     return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0 || n_chunks == 0) return B200GNN_OK;
   GatAgg p;
   p.rowptr = rowptr; p.col = col; p.eidx = eidx; p.chunk_rowptr = chunk_rowptr; p.hub_rows = hub_rows;
+  p.hub_segptr = hub_segptr; p.ws = hub_workspace;
   p.a = a; p.ft = ft; p.out = out; p.ldf = ldf; p.ldo = ldo;
-  p.n_chunks = (int32_t)n_chunks; p.n_hub = (int32_t)n_hub; p.hub_threshold = hub_threshold;
+  p.n_chunks = (int32_t)n_chunks; p.n_hub = (int32_t)n_hub; p.n_seg = (int32_t)(n_hub > 0 ? n_seg : 0); p.seg_len = seg_len;
+  p.hub_threshold = hub_threshold;
   p.H = (int32_t)H; p.D = (int32_t)D; p.K = (int32_t)K;
   cudaStream_t st = (cudaStream_t)stream;
   // a vector must not straddle two heads: D % W == 0
@@ -578,16 +612,19 @@ extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* co
                                         const float* dout, int64_t ldd, const float* el, const float* er, int64_t n_rows,
                                         int64_t H, int64_t D, float negative_slope, float* dpre, float* der,
                                         const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
-                                        const int32_t* hub_rows, int64_t n_hub, void* stream) {
+                                        int32_t seg_len, const int32_t* hub_rows, const int32_t* hub_segptr, int64_t n_hub,
+                                        int64_t n_seg, float* hub_workspace, void* stream) {
   const int64_t K = H * D;
   if (!rowptr || !a || !ft || !dout || !el || !dpre || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < K || ldd < K ||
-      !chunk_rowptr || n_chunks < 0 || n_hub < 0 || (n_hub > 0 && !hub_rows))
+      !chunk_rowptr || n_chunks < 0 || n_hub < 0 || n_seg < n_hub ||
+      (n_hub > 0 && (!hub_rows || !hub_segptr || !hub_workspace || seg_len <= 0)))
     return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0 || n_chunks == 0) return B200GNN_OK;
   GatBwd p;
   p.rowptr = rowptr; p.col = col; p.a = a; p.ft = ft; p.dout = dout; p.el = el; p.er = er; p.dpre = dpre; p.der = der;
-  p.chunk_rowptr = chunk_rowptr; p.hub_rows = hub_rows;
+  p.chunk_rowptr = chunk_rowptr; p.hub_rows = hub_rows; p.hub_segptr = hub_segptr; p.ws = hub_workspace;
   p.ldf = ldf; p.ldd = ldd; p.n_rows = n_rows; p.n_chunks = (int32_t)n_chunks; p.n_hub = (int32_t)n_hub;
+  p.n_seg = (int32_t)(n_hub > 0 ? n_seg : 0); p.seg_len = seg_len;
   p.hub_threshold = hub_threshold; p.H = (int32_t)H; p.D = (int32_t)D; p.K = (int32_t)K; p.slope = negative_slope;
   cudaStream_t st = (cudaStream_t)stream;
   if (D % 4 == 0 && ldf % 4 == 0 && ldd % 4 == 0 && aligned_to(ft, 16) && aligned_to(dout, 16) && K <= 4 * 32 * GAT_MAXJ)

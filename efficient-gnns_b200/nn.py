@@ -329,7 +329,7 @@ class _GatAggregate(torch.autograd.Function):
                                              dout.data_ptr(), dout.stride(0), el.data_ptr(),
                                              None if er is None else er.data_ptr(), G.n_rows, H, D, ctx.slope, dpre.data_ptr(),
                                              None if der is None else der.data_ptr(), G.chunk_rowptr.data_ptr(), G.n_chunks,
-                                             G.hub_threshold, G.hub_rows.data_ptr() if G.n_hub else None, G.n_hub, s),
+                                             *_hub_args(G, H), s),
                   "gat_bwd_rows_f32")
         Gt = st.engine_csc("value")                              # transposed graph as CSR (rows = sources)
         perm = _csr2csc_i32(st)
@@ -351,8 +351,16 @@ def _csr2csc_i32(st) -> torch.Tensor:
 def _gat_aggregate(G, eidx, a, ft, out, H, D):
     lib.check(lib.load().b200gnn_gat_aggregate_f32(
         G.rowptr.data_ptr(), G.col.data_ptr(), None if eidx is None else eidx.data_ptr(), a.data_ptr(), ft.data_ptr(),
-        ft.stride(0), out.data_ptr(), out.stride(0), G.n_rows, H, D, G.chunk_rowptr.data_ptr(), G.n_chunks, G.hub_threshold,
-        G.hub_rows.data_ptr() if G.n_hub else None, G.n_hub, lib.stream_ptr()), "gat_aggregate_f32")
+        ft.stride(0), out.data_ptr(), out.stride(0), G.n_rows, H, D, G.chunk_rowptr.data_ptr(), G.n_chunks,
+        *_hub_args(G, H * D), lib.stream_ptr()), "gat_aggregate_f32")
+
+
+def _hub_args(G, ws_width: int):
+    """(hub_threshold, seg_len, hub_rows, hub_segptr, n_hub, n_seg, workspace[n_seg * ws_width]) of a CsrGraph plan."""
+    if not G.n_hub:
+        return G.hub_threshold, G.seg_len, None, None, 0, 0, None
+    return (G.hub_threshold, G.seg_len, G.hub_rows.data_ptr(), G.hub_segptr.data_ptr(), G.n_hub, G.n_seg,
+            G.hub_workspace(ws_width).data_ptr())
 
 
 def gat_aggregate(ft, el, er, adj: SparseTensor, heads: int, negative_slope: float = 0.2, softmax_eps: float = 0.0):

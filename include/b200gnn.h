@@ -313,7 +313,9 @@ int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src,
  *                      (forward on the CSR; d ft on the transposed CSR with eidx = csr2csc)
  *   gat_bwd_rows     : given d out, writes dpre[e,h] = d loss / d (el+er)[e,h] and der[r,h]
  *   segment_sum_heads: out[r,h] = sum_e vals[eidx[e],h]  (d el over the transposed CSR)
- * H <= 16.  chunk_rowptr / hub_rows: the plans of b200gnn_csr_chunk_plan / b200gnn_csr_hub_fill.
+ * H <= 16.  chunk_rowptr / hub_rows / hub_segptr: the plans of b200gnn_csr_chunk_plan / b200gnn_csr_hub_fill
+ * (rows above hub_threshold are split into seg_len-edge segments, as in b200gnn_spmm_csr_f32).
+ * hub_workspace: n_seg*H*D floats for gat_aggregate, n_seg*H floats for gat_bwd_rows (unused when n_hub == 0).
  * ------------------------------------------------------------------ */
 int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t* col,
                                  const float* el, const float* er, int64_t n_rows,
@@ -323,16 +325,20 @@ int b200gnn_gat_aggregate_f32(const int32_t* rowptr, const int32_t* col,
                               const int32_t* eidx, const float* a, const float* ft,
                               int64_t ldf, float* out, int64_t ldo, int64_t n_rows,
                               int64_t H, int64_t D, const int32_t* chunk_rowptr,
-                              int64_t n_chunks, int32_t hub_threshold,
-                              const int32_t* hub_rows, int64_t n_hub, void* stream);
+                              int64_t n_chunks, int32_t hub_threshold, int32_t seg_len,
+                              const int32_t* hub_rows, const int32_t* hub_segptr,
+                              int64_t n_hub, int64_t n_seg, float* hub_workspace,
+                              void* stream);
 int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const float* a,
                              const float* ft, int64_t ldf, const float* dout,
                              int64_t ldd, const float* el, const float* er,
                              int64_t n_rows, int64_t H, int64_t D,
                              float negative_slope, float* dpre, float* der,
                              const int32_t* chunk_rowptr, int64_t n_chunks,
-                             int32_t hub_threshold, const int32_t* hub_rows,
-                             int64_t n_hub, void* stream);
+                             int32_t hub_threshold, int32_t seg_len,
+                             const int32_t* hub_rows, const int32_t* hub_segptr,
+                             int64_t n_hub, int64_t n_seg, float* hub_workspace,
+                             void* stream);
 int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx,
                                   const float* vals, int64_t n_rows, int64_t H,
                                   float* out, void* stream);
