@@ -41,6 +41,7 @@ class Student(torch.nn.Module):
 
 
 def main():
+    only = int(sys.argv[sys.argv.index("--only") + 1]) if "--only" in sys.argv else None
     dev = "cuda"
     ds = synthetic.make_node_dataset(synthetic.ARXIV, seed=0)
     n = ds.num_nodes
@@ -53,7 +54,7 @@ def main():
     nnz = adj.nnz()
 
     # ---- config 3: SAGE + G-CRD
-    for S in (8192, 16384):
+    for S in (8192, 16384) if only in (None, 3) else ():
         torch.manual_seed(0)
         model = Student(bnn.SAGEConv, [128, 256, 256, 40]).to(dev)
         sproj = torch.nn.Sequential(bnn.Linear(256, 256), torch.nn.BatchNorm1d(256), torch.nn.ReLU()).to(dev)
@@ -71,7 +72,9 @@ def main():
 
     # ---- config 4: GAT layer + LSP
     adj_sl = bnn._fill_diag_pattern(adj)
-    for H, D in ((8, 32), (3, 250)):
+    if only not in (None, 4, 5):
+        return
+    for H, D in ((8, 32), (3, 250)) if only in (None, 4) else ():
         torch.manual_seed(0)
         layer = bnn.DGLGATConv(128, D, num_heads=H, use_symmetric_norm=True).to(dev)
 
@@ -90,10 +93,13 @@ def main():
     def lsp_step():
         loss, _, _ = C.lpw_criterion(z, y[idx], feat, tsub, sub, "cosine", 100)
         feat.grad = None; loss.backward()
-    ms = med_time(lsp_step, 8, 3)
-    print(json.dumps(dict(config=4, what="LSP cosine (student 256-d, teacher 750-d) fwd+bwd on the train-induced subgraph",
-                          E_sub=int(sub.shape[1]), ms=ms, reference_materialised_bytes=int(sub.shape[1]) * (256 + 750) * 2 * 4)),
-          flush=True)
+    ms = med_time(lsp_step, 8, 3) if only in (None, 4) else 0.0
+    if only in (None, 4):
+        print(json.dumps(dict(config=4, what="LSP cosine (student 256-d, teacher 750-d) fwd+bwd on the train-induced subgraph",
+                              E_sub=int(sub.shape[1]), ms=ms,
+                              reference_materialised_bytes=int(sub.shape[1]) * (256 + 750) * 2 * 4)), flush=True)
+    if only not in (None, 5):
+        return
 
     # ---- config 5: MAG-shape per-relation mean aggregation (RGCN.inference formulation, mag_pyg/gnn.py:153-169)
     rels = []
