@@ -213,13 +213,14 @@ class ShardedGCNTrainer(GCNStudentTrainer):
             if l == self.L - 1:
                 ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(k_out))
             if l == 0 and self.agg_first:
-                self._linear_wgrad(0, self.AX, self.dY[0])
+                self._wgrad_async(0, self.AX, self.dY[0])
                 continue
             full = self._all_gather(self.dY[l])
             ops.spmm_csr(self.G, full, "sum", out=self.dH[l])        # Â symmetric: dH_p = Â[p,:] dY
-            self._linear_wgrad(l, inp, self.dH[l])
             if l > 0:
                 self._linear_dgrad(l, self.dH[l], self.dA[l - 1])
+            self._wgrad_async(l, inp, self.dH[l])                    # side stream: hides under BN backward + the next all-gather
+            if l > 0:
                 k = self.dims[l]
                 part, bn = self._part(k), self.bn[l - 1]
                 ops.bn_act_bwd_reduce(self.dA[l - 1], self.A[l - 1], self.Y[l - 1], bn[0], bn[1], self.p, part)
@@ -229,6 +230,7 @@ class ShardedGCNTrainer(GCNStudentTrainer):
                                      self.gb[l - 1], part, self._coef(k))
                 if self.rank != 0:      # dgamma/dbeta come from GLOBAL sums: count them once in the all-reduce below
                     self.ggamma[l - 1].zero_(); self.gbeta[l - 1].zero_()
+        self._wgrad_join()
 
     def _step_impl(self, x_pad, y_loc, train_loc, teacher_loc):
         logits = self.forward(x_pad, training=True)

@@ -52,7 +52,7 @@ class GCNStudentTrainer:
 
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
                  alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
-                 aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True,
+                 aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True, overlap_wgrad: bool = True,
                  _prebuilt_graph: Optional[CsrGraph] = None, _rows_alloc: Optional[int] = None):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         self.device = adj.device
@@ -147,6 +147,11 @@ class GCNStudentTrainer:
         self.loss_out = torch.zeros(3, device=dev)
         self.kd_part = torch.empty(2 * int(lib.load().b200gnn_kd_partials(N)), device=dev)
         self._graph = None
+        # weight gradients only feed Adam: they run on a side stream next to the BN/ReLU backward passes and the next
+        # aggregation (parallel branches of the captured graph)
+        self.overlap_wgrad = overlap_wgrad
+        self._side = torch.cuda.Stream(device=dev) if overlap_wgrad else None
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._static: Dict[str, torch.Tensor] = {}
         for k in set(dims[1:]):
             self._part(k); self._coef(k)
@@ -235,17 +240,33 @@ class GCNStudentTrainer:
             if l == self.L - 1:
                 ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(self.dims[l + 1]))
             if l == 0 and self.agg_first:
-                self._linear_wgrad(0, self.AX, self.dY[0])             # dW0 = (ÂX)ᵀ dY0, no backward aggregation
+                self._wgrad_async(0, self.AX, self.dY[0])              # dW0 = (ÂX)ᵀ dY0, no backward aggregation
                 continue
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
-            self._linear_wgrad(l, inp, self.dH[l])
             if l > 0:
                 self._linear_dgrad(l, self.dH[l], self.dA[l - 1])
+            self._wgrad_async(l, inp, self.dH[l])                      # forks after the dgrad GEMM (both want the whole SM)
+            if l > 0:
                 k = self.dims[l]
                 part = self._part(k)
                 ops.bn_act_bwd(self.dA[l - 1], self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
                                self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
                                d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
+        self._wgrad_join()
+
+    def _wgrad_async(self, l: int, inp: torch.Tensor, d_out: torch.Tensor):
+        """grad W_l on the side stream, ordered after everything enqueued so far on the current stream."""
+        if self._side is None:
+            return self._linear_wgrad(l, inp, d_out)
+        self._ev_fork.record(torch.cuda.current_stream())
+        self._side.wait_event(self._ev_fork)
+        with torch.cuda.stream(self._side):
+            self._linear_wgrad(l, inp, d_out)
+
+    def _wgrad_join(self):
+        if self._side is not None:
+            self._ev_join.record(self._side)
+            torch.cuda.current_stream().wait_event(self._ev_join)
 
     def _linear(self, l: int, inp: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None):
         """out = inp @ W_l (+bias): tcgen05 3xTF32 kernel, or cuBLAS fp32 when disabled."""
