@@ -13,7 +13,6 @@ def run(args):
     from . import lib, sparse, synthetic
     from .dist import ShardedGCNTrainer
 
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: bench prints ONE JSON line
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -142,7 +141,7 @@ def run(args):
                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 12 * world},
                 "gpu_launches": launches * args.steps * world, "gpu_launches_per_step_per_rank": launches,
                 "clocks": clk.summary(), "loss": tr.loss_out.tolist()}
-        print(json.dumps(line), flush=True)
+        B.emit_json_line(line)
     # NCCL teardown with live CUDA graphs that captured collectives can dead-lock; results are out, leave hard.
     torch.cuda.synchronize()
     import sys
