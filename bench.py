@@ -319,7 +319,7 @@ def run_single(args):
                                                "aggregations_executed": tr.aggregations_per_step(),
                                                "edges_note": "value counts the reference step's 6 aggregations (2*L*nnz); "
                                                "the engine executes layer 0 as (A_hat X) W, which needs 5"}),
-            "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel K=256 (4 of the 6 aggregations per step)",
+            "roofline": {"bound": "hbm", "kernel": "spmm_rows_pipe_kernel, K=256 aggregation (2 of the 5 aggregations the engine runs per step; the reference runs 4 of 6 at this width)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg, "ms_per_launch": k256_ms,
                          "launches_timed": len(evs), "peak_source": peak_src},
