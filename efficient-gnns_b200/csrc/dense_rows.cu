@@ -64,9 +64,10 @@ __global__ void __launch_bounds__(ROWS_THREADS) col_stats4_kernel(const float* _
 // ---------------------------------------------------------------- BatchNorm finalize (training mode)
 // partial[slots][2][K] -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale; running stats updated
 // like nn.BatchNorm1d (momentum, unbiased running variance).  fp64 accumulation of the partials.
-// Reduce partial[slots][2][K] over slots for 8 columns per CTA (32 row groups x 8 columns = 256 threads, 32-byte
-// sectors fully used, K/8 CTAs), fp64 accumulation, fixed order => deterministic.
-constexpr int FIN_COLS = 8, FIN_GROUPS = 32;
+// Reduce partial[slots][2][K] over slots for 4 columns per CTA (64 slot groups x 4 columns = 256 threads, K/4 CTAs:
+// these kernels sit on the step's critical path and are latency-bound, so more, shorter chains), fp64 accumulation,
+// fixed order => deterministic.
+constexpr int FIN_COLS = 4, FIN_GROUPS = 64;
 __device__ __forceinline__ bool finalize_reduce(const float* __restrict__ partial, int slots, int K, bool second,
                                                 double& s_out, double& q_out, int& k_out) {
   __shared__ double sh[2][FIN_GROUPS][FIN_COLS];
@@ -114,45 +115,93 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------- forward: affine + ReLU + dropout
-// out = dropout(relu(y*scale + shift)); keep iff philox uniform >= p; kept values scaled by 1/(1-p).
+// out = dropout(relu(y*scale + shift)); kept values scaled by 1/(1-p).  The keep decision of element e is a pure
+// function of (seed, offset, global element index), so masks are identical under any row sharding:
+//   P16 (p * 65536 integral, e.g. the reference's p = 0.5): Philox block b = (global float4 index) / 2 yields eight
+//       16-bit uniforms, keep iff u16 >= p * 65536 — exact for such p, and half the generator work per element
+//       (the pass is integer-bound on Philox, not HBM-bound, otherwise);
+//   else: block b = global float4 index, four 24-bit uniforms, keep iff u >= p.
+__device__ __forceinline__ float4 affine_relu4(float4 y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                               int cv, int relu) {
+  if (scale) {
+    const float4 sc = ld4(scale + 4 * cv), sh = ld4(shift + 4 * cv);
+    y.x = fmaf(y.x, sc.x, sh.x); y.y = fmaf(y.y, sc.y, sh.y);
+    y.z = fmaf(y.z, sc.z, sh.z); y.w = fmaf(y.w, sc.w, sh.w);
+  }
+  if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+  return y;
+}
+__device__ __forceinline__ uchar4 keep16(uint32_t a, uint32_t b, uint32_t thr) {
+  uchar4 m;
+  m.x = (a & 0xffffu) >= thr; m.y = (a >> 16) >= thr; m.z = (b & 0xffffu) >= thr; m.w = (b >> 16) >= thr;
+  return m;
+}
+__device__ __forceinline__ uchar4 keep24(const uint4& r, float p) {
+  uchar4 m;
+  m.x = u32_to_unit(r.x) >= p; m.y = u32_to_unit(r.y) >= p; m.z = u32_to_unit(r.z) >= p; m.w = u32_to_unit(r.w) >= p;
+  return m;
+}
+
+template <bool P16>
 __global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* __restrict__ Y, float* __restrict__ out,
                                                                   int64_t n_vec, int nvec_row,
                                                                   const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, int relu, float p,
-                                                                  uint64_t seed, uint64_t offset,
+                                                                  uint32_t thr16, uint64_t seed, uint64_t offset,
                                                                   const int32_t* __restrict__ step_dev,
                                                                   uint64_t step_mul, uint64_t index_offset) {
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (step_dev) offset += (uint64_t)(*step_dev) * step_mul;  // graph-replayable per-step offset
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % nvec_row);
-    float4 y = ld4s(Y + 4 * i);
-    if (scale) {
-      const float4 sc = ld4(scale + 4 * cv), sh = ld4(shift + 4 * cv);
-      y.x = fmaf(y.x, sc.x, sh.x); y.y = fmaf(y.y, sc.y, sh.y);
-      y.z = fmaf(y.z, sc.z, sh.z); y.w = fmaf(y.w, sc.w, sh.w);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (P16) {
+    const uint64_t g0 = index_offset, g1 = index_offset + (uint64_t)n_vec;
+    for (uint64_t b = (g0 >> 1) + (uint64_t)tid; b < ((g1 + 1) >> 1); b += (uint64_t)stride) {
+      const uint4 r = philox4x32(seed, offset, b);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint64_t g = 2 * b + half;
+        if (g < g0 || g >= g1) continue;
+        const int64_t i = (int64_t)(g - g0);
+        float4 y = affine_relu4(ld4s(Y + 4 * i), scale, shift, (int)(i % nvec_row), relu);
+        const uchar4 m = keep16(half ? r.z : r.x, half ? r.w : r.y, thr16);
+        y.x = m.x ? y.x * inv_keep : 0.f; y.y = m.y ? y.y * inv_keep : 0.f;
+        y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
+        st4(out + 4 * i, y);
+      }
     }
-    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    if (p > 0.f) {
-      const uint4 r = philox4x32(seed, offset, (uint64_t)i + index_offset);
-      y.x = (u32_to_unit(r.x) >= p) ? y.x * inv_keep : 0.f;
-      y.y = (u32_to_unit(r.y) >= p) ? y.y * inv_keep : 0.f;
-      y.z = (u32_to_unit(r.z) >= p) ? y.z * inv_keep : 0.f;
-      y.w = (u32_to_unit(r.w) >= p) ? y.w * inv_keep : 0.f;
+  } else {
+    for (int64_t i = tid; i < n_vec; i += stride) {
+      float4 y = affine_relu4(ld4s(Y + 4 * i), scale, shift, (int)(i % nvec_row), relu);
+      if (p > 0.f) {
+        const uchar4 m = keep24(philox4x32(seed, offset, (uint64_t)i + index_offset), p);
+        y.x = m.x ? y.x * inv_keep : 0.f; y.y = m.y ? y.y * inv_keep : 0.f;
+        y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
+      }
+      st4(out + 4 * i, y);
     }
-    st4(out + 4 * i, y);
   }
 }
 
 // The keep-mask the kernel above uses, materialised (tests inject it into the CPU oracle).
-__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n_vec, float p,
-                                                           uint64_t seed, uint64_t offset) {
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n_vec, float p, int p16,
+                                                           uint32_t thr16, uint64_t seed, uint64_t offset) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 r = philox4x32(seed, offset, (uint64_t)i);
     uchar4 m;
-    m.x = u32_to_unit(r.x) >= p; m.y = u32_to_unit(r.y) >= p; m.z = u32_to_unit(r.z) >= p; m.w = u32_to_unit(r.w) >= p;
+    if (p16) {
+      const uint4 r = philox4x32(seed, offset, (uint64_t)i >> 1);
+      m = keep16((i & 1) ? r.z : r.x, (i & 1) ? r.w : r.y, thr16);
+    } else {
+      m = keep24(philox4x32(seed, offset, (uint64_t)i), p);
+    }
     reinterpret_cast<uchar4*>(mask)[i] = m;
   }
+}
+
+// p * 65536 integral (and p > 0): the 16-bit decision path is exact
+static inline bool dropout_p16(float p, uint32_t& thr16) {
+  const double t = (double)p * 65536.0;
+  thr16 = (uint32_t)t;
+  return p > 0.f && t == (double)thr16;
 }
 
 // ---------------------------------------------------------------- backward of BN(train)+ReLU+dropout
@@ -317,8 +366,15 @@ extern "C" int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64
     return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
   const int64_t n_vec = n_rows * (K / 4);
-  affine_relu_dropout_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-      Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, seed, offset, step_dev, step_mul, row_offset * (uint64_t)(K / 4));
+  uint32_t thr16 = 0;
+  if (dropout_p16(p, thr16))
+    affine_relu_dropout_kernel<true><<<grid_for((n_vec + 1) / 2 + 1, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+        Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, thr16, seed, offset, step_dev, step_mul,
+        row_offset * (uint64_t)(K / 4));
+  else
+    affine_relu_dropout_kernel<false><<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, 0u, seed, offset, step_dev, step_mul,
+        row_offset * (uint64_t)(K / 4));
   return check_launch();
 }
 
@@ -327,7 +383,9 @@ extern "C" int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K,
   if (!rows_ok(n_rows, K) || !mask || p < 0.f || p >= 1.f) return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
   const int64_t n_vec = n_rows * (K / 4);
-  dropout_mask_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(mask, n_vec, p, seed, offset);
+  uint32_t thr16 = 0;
+  const int p16 = dropout_p16(p, thr16) ? 1 : 0;
+  dropout_mask_kernel<<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(mask, n_vec, p, p16, thr16, seed, offset);
   return check_launch();
 }
 

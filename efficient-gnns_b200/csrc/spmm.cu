@@ -532,11 +532,43 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_narrow_kernel(const
 
 // Sum a hub row's segment partials in segment order, apply the epilogue.
 __global__ void __launch_bounds__(256) spmm_hub_finalize_kernel(const SpmmParams p) {
+  __shared__ float4 sh[256];
   const int h = blockIdx.x;
   const int row = __ldg(p.hub_rows + h);
   const int s0 = __ldg(p.hub_segptr + h), s1 = __ldg(p.hub_segptr + h + 1);
   const int deg = __ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row);
   float* stat = p.stat_partial ? p.stat_partial + (size_t)(p.main_grid + h) * 2 * p.K : nullptr;
+  const int nvec = p.K >> 2;
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if ((p.K & 3) == 0 && nvec <= 256 && (p.ldy & 3) == 0 && al16(p.Y) && al16(p.hub_ws) && (!stat || al16(stat))) {
+    // segment-parallel: G groups of nvec lanes, group g adds segments s0+g, s0+g+G, ...; groups combined in order
+    const int G = min(256 / nvec, 16);
+    const int v = threadIdx.x % nvec, g = threadIdx.x / nvec;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < G)
+      for (int s = s0 + g; s < s1; s += G) {
+        const float4 x = *reinterpret_cast<const float4*>(p.hub_ws + (size_t)s * p.K + 4 * v);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (g != 0) return;
+    for (int j = 1; j < G; ++j) {
+      const float4 x = sh[j * nvec + v];
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    if (p.mean) { const float d = (float)max(deg, 1); acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d; }
+    if (p.bias) {
+      acc.x += __ldg(p.bias + 4 * v); acc.y += __ldg(p.bias + 4 * v + 1);
+      acc.z += __ldg(p.bias + 4 * v + 2); acc.w += __ldg(p.bias + 4 * v + 3);
+    }
+    *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + 4 * v) = acc;
+    if (stat) {
+      *reinterpret_cast<float4*>(stat + 4 * v) = acc;
+      *reinterpret_cast<float4*>(stat + p.K + 4 * v) = make_float4(acc.x * acc.x, acc.y * acc.y, acc.z * acc.z, acc.w * acc.w);
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
     float acc = 0.f;
     for (int s = s0; s < s1; ++s) acc += p.hub_ws[(size_t)s * p.K + k];

@@ -148,7 +148,10 @@ int b200gnn_bn_finalize_f32(const float* partial, int64_t slots, int64_t K,
  * CUDA graph draws a fresh mask on every replay;
  * row_offset: global index of row 0 of Y (node-parallel shards draw the mask
  * of their own rows of the global matrix; 0 on a single GPU);
- * b200gnn_dropout_mask_u8 materialises the mask of a given effective offset. */
+ * b200gnn_dropout_mask_u8 materialises the mask of a given effective offset.
+ * Uniforms: when p*65536 is integral (the reference's p = 0.5) eight 16-bit
+ * uniforms per Philox block, keep iff u16 >= p*65536 (exact); otherwise four
+ * 24-bit uniforms per block, keep iff u >= p. */
 int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows,
                                     int64_t K, const float* scale,
                                     const float* shift, int relu, float p,
