@@ -27,16 +27,29 @@ namespace b200gnn {
 namespace gemm {
 using namespace tc;
 
-constexpr int BM = 128, BN = 128, BK = 32, UMMA_K = 8;
-constexpr int STAGES = 3, ACC_STAGES = 2;
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
+constexpr int ACC_STAGES = 2;
 constexpr int THREADS = 384;
-constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (A and B tiles are both 128 x 32 fp32)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB: one 128 x 32 fp32 A tile
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_LD = 36;                              // floats per staged row (144 B: 16-byte aligned, conflict-free)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;          // one 32x32 staging block per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + slack for 1024 B alignment
-constexpr int TMEM_COLS = ACC_STAGES * BN;              // 256
+
+// Tile shape: BN_T output columns per tile (the UMMA N) and the number of smem stages that fit.
+//   Wide  <128, 3>: 3 x 64 KB stages, 2 x 128 TMEM columns.
+//   Narrow <48, 4>: for N <= 48 (the 40-class logits): the B tiles shrink to 6 KB, one more stage fits (the narrow
+//                   GEMM is bound by the DRAM latency of A, so depth is what it needs) and the MMAs do 3/8 of the work.
+template <int BN_T, int NSTAGE>
+struct Cfg {
+  static constexpr int BN = BN_T, STAGES = NSTAGE;
+  static constexpr int B_TILE_BYTES = BN_T * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+  static constexpr int ACC_STRIDE = BN_T <= 64 ? 64 : 128;                        // TMEM columns per accumulator
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE;                       // 128 or 256 (power of two)
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + slack for 1024 B alignment
+  static_assert(B_TILE_BYTES % 1024 == 0 && BN_T % 16 == 0 && BN_T <= 256, "tile shape");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -50,6 +63,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // tcgen05 instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN.
+template <int BN>
 __device__ __forceinline__ uint32_t make_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -61,9 +75,12 @@ struct Params {
   int32_t M, N, K;
 };
 
+template <class C>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const Params p) {
+  constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE_BYTES = C::B_TILE_BYTES;
+  constexpr int TMEM_COLS = C::TMEM_COLS, ACC_STRIDE = C::ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -105,10 +122,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], 3 * TILE_BYTES);
+          mbar_expect_tx(&full[s], TILE_BYTES + 2 * B_TILE_BYTES);
           tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
           tma_load_2d(&tmBhi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
-          tma_load_2d(&tmBlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+          tma_load_2d(&tmBlo, &full[s], st + 2 * TILE_BYTES + B_TILE_BYTES, kb * BK, n0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -116,12 +133,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc();
+      const uint32_t idesc = make_idesc<BN>();
       int s = 0; uint32_t ph = 0; int a = 0; uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[a], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_STRIDE);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           mbar_wait(&split[s], ph);
@@ -132,7 +149,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t koff = k * UMMA_K * 4;  // 32 B per K-step inside the 128 B swizzle atom
             const uint64_t a_hi = make_smem_desc(st + koff), a_lo = make_smem_desc(st + TILE_BYTES + koff);
             const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES + koff);
-            const uint64_t b_lo = make_smem_desc(st + 3 * TILE_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc(st + 2 * TILE_BYTES + B_TILE_BYTES + koff);
             mma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | k) != 0);
             mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
             mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
@@ -178,9 +195,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < (BN + 31) / 32; ++c) {    // a partial last chunk reads spare columns of the accumulator's stride
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ACC_STRIDE + c * 32), r);
         const int col0 = n0 + c * 32;
         if (vec_ok && col0 + 32 <= p.N) {
           // Transpose the warp's 32x32 block through shared memory so that global stores are whole 128-byte row
@@ -239,17 +256,39 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
-// [rows, cols] fp32 row-major with leading dimension ld -> boxes of 32 columns x 128 rows, 128B swizzle, zero OOB fill
-static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+// [rows, cols] fp32 row-major with leading dimension ld -> boxes of 32 columns x box_rows rows, 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class C>
+static int launch(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, const Params& p,
+                  cudaStream_t stream) {
+  CUtensorMap tA, tBh, tBl;
+  if (!make_map(&tA, A, p.M, p.K, lda, BM) || !make_map(&tBh, B_hi, p.N, p.K, ldb, C::BN) ||
+      !make_map(&tBl, B_lo, p.N, p.K, ldb, C::BN))
+    return B200GNN_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + C::BN - 1) / C::BN);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_tf32x3_kernel<C><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tA, tBh, tBl, p);
+  return check_launch();
 }
 
 }  // namespace gemm
@@ -276,24 +315,8 @@ extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float*
   // TMA: 16-byte aligned bases and row pitches
   if (lda % 4 || ldb % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16))
     return B200GNN_ERR_UNSUPPORTED;
-  CUtensorMap tA, tBh, tBl;
-  if (!gemm::make_map(&tA, A, M, K, lda) || !gemm::make_map(&tBh, B_hi, N, K, ldb) ||
-      !gemm::make_map(&tBl, B_lo, N, K, ldb))
-    return B200GNN_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm::gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         gemm::SMEM_BYTES);
-    if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
-    attr_set = true;
-  }
   gemm::Params p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
-  const int tiles = (int)(((M + gemm::BM - 1) / gemm::BM) * ((N + gemm::BN - 1) / gemm::BN));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = tiles < sms ? tiles : sms;
-  gemm::gemm_tf32x3_kernel<<<grid, gemm::THREADS, gemm::SMEM_BYTES, (cudaStream_t)stream>>>(tA, tBh, tBl, p);
-  return check_launch();
+  if (N <= 48) return gemm::launch<gemm::Cfg<48, 4>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
+  return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
 }

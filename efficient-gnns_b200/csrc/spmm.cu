@@ -41,7 +41,7 @@ struct SpmmParams {
   int64_t ldx, ldy;  // in floats
   int32_t n_rows, K, nvec;
   int32_t hub_threshold, seg_len, n_hub, n_seg, n_chunks;
-  int32_t mean, stream_store, main_grid, l2_hint;
+  int32_t mean, stream_store, main_grid;
 };
 
 struct LaneMap {
@@ -293,18 +293,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
-// The gathered operand is the only stream with reuse (every row of X is read ~deg times): ask L2 to keep it
-// (evict_last) while col/val/Y stream through.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, uint64_t pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "l"(pol)
-               : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -312,6 +300,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int CH, bool HAS_VAL, bool STATS>
 __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const int cta, float* s_stat, float4* ring_all) {
   constexpr int D = PIPE_BYTES / (CH * 512);     // ring depth in neighbour rows (CH=2 -> 8, CH=1 -> 16)
+  constexpr int G = D >= 8 ? 4 : 2, NG = D / G;   // cp.async group = G edges; NG groups in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* ring = ring_all + (size_t)warp * (PIPE_BYTES / 16);   // slot s: ring[s*CH*32 + j*32 + lane]
   const float4* Xv = reinterpret_cast<const float4*>(p.X);
@@ -325,8 +314,6 @@ __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const i
   const int chunk = cta * SPMM_WARPS + warp;
   const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
   const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
-  const uint64_t pol = l2_policy_evict_last();
-  const bool hint = p.l2_hint != 0;
 
   auto flush = [&](int row, int deg, float4 (&acc)[CH]) {
 #pragma unroll
@@ -381,74 +368,68 @@ __device__ __forceinline__ void spmm_chunk_cta_pipe(const SpmmParams& p, const i
     }
     if (n == 0) continue;
 
-    // two 32-edge windows of (col,val): A = consume batch, B = the next one
-    int cA, cB; float vA, vB;
-    {
-      const int eA = e_lo + lane, eB = e_lo + 32 + lane;
-      cA = eA < e_hi ? __ldg(p.col + eA) : 0;
-      cB = eB < e_hi ? __ldg(p.col + eB) : 0;
-      vA = HAS_VAL ? (eA < e_hi ? __ldg(p.val + eA) : 0.f) : 1.f;
-      vB = HAS_VAL ? (eB < e_hi ? __ldg(p.val + eB) : 0.f) : 1.f;
-    }
-    auto issue = [&](int jj) {             // copy neighbour row of edge jj (relative) into ring slot jj % D
-      if (jj < n) {
-        const int w = jj & 63;             // position inside the 64-edge (A|B) window
-        const int cc = (w < 32) ? __shfl_sync(FULL_MASK, cA, w) : __shfl_sync(FULL_MASK, cB, w - 32);
-        const float4* src = Xv + (size_t)cc * ldxv + lane;
-        float4* dst = ring + (jj % D) * (CH * 32) + lane;
+    // Two cursors over the run's edges, each with a 32-edge register window: the issue side reads `col` (cI), the consume
+    // side reads `val` (vA); both advance in groups of G edges, so window reloads and ring slots are decided per group and
+    // the slot index is a compile-time constant inside the unrolled body.  One cp.async group per G edges, NG groups
+    // (= D neighbour rows) in flight per warp.
+    int cI = 0;
+    float vA = 1.f;
+    auto issue_group = [&](int jg, int slot0) {      // edges jg..jg+G-1 (relative to e_lo) -> slots slot0..slot0+G-1
+      if ((jg & 31) == 0) { const int e = e_lo + jg + lane; cI = e < e_hi ? __ldg(p.col + e) : 0; }
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          if (hint) cp_async16_hint(dst + 32 * j, src + 32 * j, pol); else cp_async16(dst + 32 * j, src + 32 * j);
-        }
-      }
-      cp_async_commit();                   // always commit: keeps the group count uniform
-    };
-    // NOTE: window positions are relative to the batch base jb (multiple of 32); issue() is only ever called
-    // with jj in [jb, jb+64), which the D <= 32 look-ahead guarantees.
-#pragma unroll 1
-    for (int i = 0; i < D; ++i) issue(i);
-
-    int jb = 0;                            // base of window A (relative edge index)
-#pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-      if (j - jb == 32) {                  // advance the windows: A <- B, B <- next 32 edges
-        jb += 32;
-        cA = cB; vA = vB;
-        const int eB = e_lo + jb + 32 + lane;
-        cB = eB < e_hi ? __ldg(p.col + eB) : 0;
-        vB = HAS_VAL ? (eB < e_hi ? __ldg(p.val + eB) : 0.f) : 1.f;
-      }
-      cp_async_wait<D - 1>();              // the copy of edge j has landed (groups retire in order)
-      const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, j - jb) : 1.f;
-      const float4* slot = ring + (j % D) * (CH * 32) + lane;
-      float4 x[CH];
-#pragma unroll
-      for (int jj = 0; jj < CH; ++jj) x[jj] = slot[32 * jj];
-#pragma unroll
-      for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, x[jj]);
-      // refill the slot just consumed (the loads above have been consumed by the FMAs)
-      {
-        const int jn = j + D;
-        if (jn < n) {
-          const int wpos = jn - jb;        // < 64 because D <= 32
-          const int cc = (wpos < 32) ? __shfl_sync(FULL_MASK, cA, wpos) : __shfl_sync(FULL_MASK, cB, wpos - 32);
+      for (int u = 0; u < G; ++u) {
+        if (jg + u < n) {                            // warp-uniform
+          const int cc = __shfl_sync(FULL_MASK, cI, (jg + u) & 31);
           const float4* src = Xv + (size_t)cc * ldxv + lane;
-          float4* dst = ring + (jn % D) * (CH * 32) + lane;
+          float4* dst = ring + (slot0 + u) * (CH * 32) + lane;
 #pragma unroll
-          for (int jj = 0; jj < CH; ++jj) {
-            if (hint) cp_async16_hint(dst + 32 * jj, src + 32 * jj, pol); else cp_async16(dst + 32 * jj, src + 32 * jj);
-          }
+          for (int jj = 0; jj < CH; ++jj) cp_async16(dst + 32 * jj, src + 32 * jj);
         }
-        cp_async_commit();
       }
-      // row boundaries (also flushes empty rows that follow)
-      const int e_next = e_lo + j + 1;
-      while (r < run_end && rend == e_next) {
+      cp_async_commit();                             // always commit: keeps the group count uniform
+    };
+    auto boundary = [&]() {                          // the current row is complete: store it (+ empty rows that follow)
+      do {
         flush(r, rend - row_beg, acc);
         row_beg = rend;
         ++r;
         if (r < run_end) rend = row_end_of(r);
+      } while (r < run_end && rend == row_beg);
+    };
+    auto consume_group = [&](int j0, int slot0) {    // j0 < n
+      if (HAS_VAL && (j0 & 31) == 0) { const int e = e_lo + j0 + lane; vA = e < e_hi ? __ldg(p.val + e) : 0.f; }
+      const float4* sbase = ring + slot0 * (CH * 32) + lane;
+      const int cnt = min(G, n - j0);
+      int done = 0;
+      while (done < cnt) {                           // pieces of the group that lie in one row (all warp-uniform)
+        const int room = rend - (e_lo + j0 + done);  // >= 1: edges left in the current row
+        const int take = min(cnt - done, room);
+        if (take == G) {                             // common case: the whole group inside one row
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, (j0 + u) & 31) : 1.f;
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, sbase[u * (CH * 32) + 32 * jj]);
+          }
+        } else {
+#pragma unroll 1
+          for (int u = done; u < done + take; ++u) {
+            const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, (j0 + u) & 31) : 1.f;
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, sbase[u * (CH * 32) + 32 * jj]);
+          }
+        }
+        done += take;
+        if (take == room) boundary();
       }
+    };
+#pragma unroll
+    for (int g = 0; g < NG; ++g) issue_group(g * G, g * G);
+#pragma unroll 1
+    for (int j = 0, s0 = 0; j < n; j += G, s0 = (s0 + G) & (D - 1)) {
+      cp_async_wait<NG - 1>();                       // the oldest group (edges j ..) has landed; groups retire in order
+      consume_group(j, s0);
+      issue_group(j + D, s0);                        // refill the slots just consumed (their loads fed the FMAs above)
     }
     cp_async_wait<0>();
   }
@@ -739,7 +720,7 @@ __global__ void __launch_bounds__(256) chunk_plan_kernel(const int32_t* __restri
 using namespace b200gnn;
 
 // 0 = automatic (pipelined kernel where eligible), 1 = always the register-staged kernel (tuning / A-B tests)
-static int g_spmm_variant = 0;  // 3 = pipelined without the L2 hint
+static int g_spmm_variant = 0;
 extern "C" void b200gnn_spmm_set_variant(int v) { g_spmm_variant = v; }
 
 extern "C" int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz, int32_t row_cost) {
@@ -805,7 +786,6 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   p.mean = reduce == B200GNN_REDUCE_MEAN;
   p.stream_store = (n_rows * K * 4 > (int64_t)64 << 20) ? 1 : 0;
   p.main_grid = (int32_t)((n_chunks + SPMM_WARPS - 1) / SPMM_WARPS);
-  p.l2_hint = (g_spmm_variant == 3) ? 0 : 1;     // variant 3: pipelined kernel without the L2 evict_last hint (A/B)
 
   // widest vector type the layout allows
   int W = 1;
@@ -822,7 +802,7 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   // K=128 (0.26 vs 0.23 ms: per-edge bookkeeping is amortised over half the bytes), so it is used from K=256 up;
   // variant 2 forces it for K=128 too.
   const bool pipe_ok = (W == 4) && g_spmm_variant != 1 &&
-                       (p.nvec == 64 || p.nvec == 128 || (p.nvec == 32 && g_spmm_variant == 2));
+                       (p.nvec == 32 || p.nvec == 64 || p.nvec == 128);
   const bool narrow_ok = (W == 4) && p.nvec <= 16 && !p.stat_partial && g_spmm_variant != 1;
   if (narrow_ok) {
     rc = B200GNN_OK;

@@ -102,8 +102,8 @@ int b200gnn_csr_hub_fill(const int32_t* rowptr, int64_t n_rows,
  * ------------------------------------------------------------------ */
 int64_t b200gnn_spmm_stat_slots(int64_t n_chunks, int64_t n_hub);
 /* Kernel selection for tuning / A-B measurement: 0 = automatic (cp.async-pipelined kernel for K in
- * {256,512}, register-staged kernel otherwise), 1 = always the register-staged kernel, 2 = pipelined
- * also for K=128. */
+ * {128,256,512}, multi-row kernel for K <= 64, register-staged kernel otherwise), 1 = always the
+ * register-staged kernel. */
 void b200gnn_spmm_set_variant(int variant);
 int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col,
                          const float* val, const float* X, int64_t ldx,
