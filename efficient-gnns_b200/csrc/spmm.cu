@@ -484,14 +484,24 @@ __device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const
     if (deg > p.hub_threshold) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int e = beg;
-    for (; e + 4 <= end; e += 4) {
-      int c[4]; float w[4]; float4 x[4];
+    if (e + 4 <= end) {                              // software-pipelined: the next batch's (col,val) load overlaps this batch's gathers
+      int c[4]; float w[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + u); w[u] = HAS_VAL ? __ldg(p.val + e + u) : 1.f; }
+      for (; e + 4 <= end; e += 4) {
+        float4 x[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
+        for (int u = 0; u < 4; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
+        float wc[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) vfma(acc, w[u], x[u]);
+        for (int u = 0; u < 4; ++u) wc[u] = w[u];
+        if (e + 8 <= end) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + 4 + u); w[u] = HAS_VAL ? __ldg(p.val + e + 4 + u) : 1.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vfma(acc, wc[u], x[u]);
+      }
     }
     for (; e < end; ++e) {
       const int c = __ldg(p.col + e);
