@@ -400,12 +400,13 @@ class DGLGATConv(torch.nn.Module):
         H, D = self._num_heads, self._out_feats
         h = self.feat_drop(feat)
         ft = self.fc(h).view(-1, H, D)
+        ft_dst = ft                    # models.py:187-188: the destination side keeps the raw projection (er is not degree-scaled)
         st = adj_t.storage
         if self._use_symmetric_norm:
             out_deg = torch.bincount(st.col(), minlength=adj_t.size(1)).float().clamp(min=1)
             ft = ft * out_deg.pow(-0.5).view(-1, 1, 1)
         el = (ft * self.attn_l).sum(-1)
-        er = (ft * self.attn_r).sum(-1) if self.attn_r is not None else None
+        er = (ft_dst * self.attn_r).sum(-1) if self.attn_r is not None else None
         rst = gat_aggregate(ft.reshape(-1, H * D), el, er, adj_t, H, self._slope, 0.0).view(-1, H, D)
         if self._use_symmetric_norm:
             rst = rst * st.rowcount().float().clamp(min=1).pow(0.5).view(-1, 1, 1)

@@ -121,3 +121,24 @@ def projection_gcd(x, rowptr, col, val, lin_w, lin_b, conv_w, conv_b, gamma, bet
     gcn-normalised adjacency (the reference's conv is non-cached, i.e. it re-derives the same normalisation every call)."""
     h = F.linear(x, lin_w, lin_b) + gcn_conv(x, rowptr, col, val, conv_w, conv_b)
     return torch.relu(batch_norm_train(h, gamma, beta))
+
+
+def dgl_gat_conv(x, row, col, n: int, fc_w, attn_l, attn_r, res_w, heads: int, negative_slope: float = 0.2,
+                 symmetric_norm: bool = True):
+    """The reference's DGL GATConv.forward (arxiv_dgl/models.py:154-236) without the stochastic teacher-training dropouts:
+    ft = fc(x) [* out_deg^-1/2]; el = <ft, attn_l>, er = <fc(x), attn_r> (destination side NOT rescaled); a = edge_softmax(leaky_relu(el[src] + er[dst]));
+    rst = sum_e a ft[src] [* in_deg^+1/2 — the exponent the reference uses, :218-223] (+ res_fc(x)).  Returns [n, H, D]."""
+    H = heads
+    D = fc_w.shape[0] // H
+    ft = F.linear(x, fc_w).view(-1, H, D)
+    ft_dst = ft                              # :187-188: feat_dst is bound before feat_src is rescaled, so er sees the raw projection
+    if symmetric_norm:
+        ft = ft * torch.bincount(col, minlength=n).clamp(min=1).to(x.dtype).pow(-0.5).view(-1, 1, 1)
+    el = (ft * attn_l).sum(-1)
+    er = (ft_dst * attn_r).sum(-1) if attn_r is not None else None
+    rst = gat_aggregate(ft.reshape(-1, H * D), el, er, row, col, n, H, negative_slope, 0.0).view(-1, H, D)
+    if symmetric_norm:
+        rst = rst * torch.bincount(row, minlength=n).clamp(min=1).to(x.dtype).pow(0.5).view(-1, 1, 1)
+    if res_w is not None:
+        rst = rst + F.linear(x, res_w).view(x.shape[0], -1, D)
+    return rst

@@ -34,6 +34,11 @@ def golden_model():
     return torch.load(GOLDEN / "model_arxiv.pt")
 
 
+@pytest.fixture(scope="session")
+def golden_gat():
+    return torch.load(GOLDEN / "gat_arxiv.pt")
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max-norm relative error max|a-b| / max|b| (SURVEY.md §8c parity metric)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

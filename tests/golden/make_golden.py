@@ -9,6 +9,9 @@ operators come from oracle/ (the CPU restatement).  What the fixtures therefore 
     computed BY THE REFERENCE FILE; only `softmax` (lpw) is a restated dependency.
   * model_*.pt      — logits / out_feat / parameter gradients of the reference's `GCN` and `SAGE` classes
     computed BY THE REFERENCE FILE on restated GCNConv / SAGEConv operators.
+  * gat_arxiv.pt    — output / gradients of the reference's own DGL `GATConv` class (arxiv_dgl/models.py:95-236) computed
+    BY THE REFERENCE FILE on a stand-in `dgl` whose four graph primitives (apply_edges(u_add_v|copy_u), edge_softmax,
+    update_all(u_mul_e, sum), in/out_degrees) are restated with plain torch index ops.
 Both oracle/ (tests, -m "not gpu") and the CUDA path (tests, -m gpu) must reproduce them.
 """
 from __future__ import annotations
@@ -96,6 +99,66 @@ def install_stubs():
     tg.transforms = mod("torch_geometric.transforms", ToSparseTensor=na)
     ogb = mod("ogb")
     ogb.nodeproppred = mod("ogb.nodeproppred", PygNodePropPredDataset=na, Evaluator=na)
+
+
+class _DGLGraph:
+    """Homogeneous graph stand-in: edges src[e] -> dst[e]; the primitives GATConv.forward uses, in plain torch."""
+
+    is_block = False
+
+    def __init__(self, src, dst, n):
+        self.src, self.dst, self.n = src, dst, n
+        self.ndata, self.edata = {}, {}
+        self.srcdata = self.dstdata = self.ndata
+
+    def local_scope(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            nd, ed = dict(self.ndata), dict(self.edata)
+            try:
+                yield
+            finally:
+                self.ndata.clear(); self.ndata.update(nd); self.edata.clear(); self.edata.update(ed)
+        return scope()
+
+    def in_degrees(self): return torch.bincount(self.dst, minlength=self.n)
+    def out_degrees(self): return torch.bincount(self.src, minlength=self.n)
+    def number_of_edges(self): return int(self.src.numel())
+    def number_of_dst_nodes(self): return self.n
+
+    def apply_edges(self, f):
+        if f[0] == "u_add_v":
+            self.edata[f[3]] = self.srcdata[f[1]][self.src] + self.dstdata[f[2]][self.dst]
+        elif f[0] == "copy_u":
+            self.edata[f[2]] = self.srcdata[f[1]][self.src]
+        else:
+            raise NotImplementedError(f)
+
+    def update_all(self, msg, red):
+        assert msg[0] == "u_mul_e" and red[0] == "sum" and msg[3] == red[1]
+        m = self.srcdata[msg[1]][self.src] * self.edata[msg[2]]
+        self.dstdata[red[2]] = torch.zeros((self.n,) + tuple(m.shape[1:]), dtype=m.dtype).index_add_(0, self.dst, m)
+
+
+def install_dgl_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    dgl = mod("dgl")
+    dgl.function = mod("dgl.function", u_add_v=lambda a, b, o: ("u_add_v", a, b, o), copy_u=lambda u, o: ("copy_u", u, o),
+                       u_mul_e=lambda u, e, o: ("u_mul_e", u, e, o), sum=lambda m, o: ("sum", m, o))
+    dgl.nn = mod("dgl.nn")
+    dgl.nn.pytorch = mod("dgl.nn.pytorch", GraphConv=None)
+    dgl.nn.pytorch.utils = mod("dgl.nn.pytorch.utils", Identity=torch.nn.Identity)
+    dgl._ffi = mod("dgl._ffi")
+    dgl._ffi.base = mod("dgl._ffi.base", DGLError=RuntimeError)
+    dgl.ops = mod("dgl.ops", edge_softmax=lambda g, e, eids=None: oo.segment_softmax(e, g.dst, g.n))
+    dgl.utils = mod("dgl.utils", expand_as_pair=lambda x: x if isinstance(x, tuple) else (x, x))
 
 
 def small_graph(n=240, e=1400, seed=3):
@@ -190,6 +253,25 @@ def main():
                               grads={k: p.grad.detach().clone() for k, p in pg.named_parameters()})
     torch.save(dict(edge_index_directed=torch.from_numpy(ei), sym_row=torch.from_numpy(r), sym_col=torch.from_numpy(c),
                     x=x, train_idx=train_idx, sub_edge_index=sub_ei, models=models), OUT / "model_arxiv.pt")
+    # ---- the reference's DGL GATConv layer (arxiv_dgl/models.py:95-236) on the symmetric graph + self-loops
+    install_dgl_stubs()
+    sys.path.insert(0, str(REF / "arxiv_dgl"))
+    dgl_models = importlib.import_module("models")
+    rs, cs, _ = og.fill_diag(r, c, np.ones(r.shape[0], dtype=np.float32), n)       # row = destination, col = source
+    graph = _DGLGraph(torch.from_numpy(cs), torch.from_numpy(rs), n)
+    gat = {}
+    for name, kw in (("attn_dst", dict(use_attn_dst=True)), ("no_attn_dst", dict(use_attn_dst=False))):
+        torch.manual_seed(3)
+        layer = dgl_models.GATConv(16, 8, num_heads=3, residual=True, use_symmetric_norm=True, **kw)
+        layer.train()
+        xin = x.clone().requires_grad_(True)
+        wout = torch.randn(n, 3, 8, generator=g)
+        out = layer(graph, xin)
+        (out * wout).sum().backward()
+        gat[name] = dict(state={k: v.detach().clone() for k, v in layer.state_dict().items()}, out=out.detach(), w=wout,
+                         d_x=xin.grad.detach().clone(),
+                         grads={k: p.grad.detach().clone() for k, p in layer.named_parameters()})
+    torch.save(dict(row=torch.from_numpy(rs), col=torch.from_numpy(cs), x=x, layers=gat), OUT / "gat_arxiv.pt")
     print("wrote", [p.name for p in OUT.glob("*.pt")])
 
 

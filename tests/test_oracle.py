@@ -171,6 +171,21 @@ def test_oracle_projection_gcd_reproduces_reference_fixture(golden_model):
         assert rel_err(st[k].grad, m["grads"][k]) < 5e-5, k
 
 
+@pytest.mark.parametrize("name", ["attn_dst", "no_attn_dst"])
+def test_oracle_gat_layer_reproduces_reference_gatconv_fixture(golden_gat, name):
+    """oracle.nn.dgl_gat_conv vs the output / gradients of the reference's own GATConv class (tests/golden/make_golden.py)."""
+    G, m = golden_gat, golden_gat["layers"][name]
+    n = G["x"].shape[0]
+    st = {k: t.clone().requires_grad_(True) for k, t in m["state"].items()}
+    x = G["x"].clone().requires_grad_(True)
+    out = onn.dgl_gat_conv(x, G["row"], G["col"], n, st["fc.weight"], st["attn_l"], st.get("attn_r"), st["res_fc.weight"], 3)
+    assert rel_err(out, m["out"]) < 1e-5
+    (out * m["w"]).sum().backward()
+    assert rel_err(x.grad, m["d_x"]) < 5e-5
+    for k, t in st.items():
+        assert rel_err(t.grad, m["grads"][k]) < 5e-5, k
+
+
 def test_dgl_graph_conv_and_sign_average_against_dense():
     """oracle.nn.dgl_graph_conv_both / neighbor_average_features vs an explicit dense adjacency."""
     from oracle import nn as onn
