@@ -142,3 +142,38 @@ def dgl_gat_conv(x, row, col, n: int, fc_w, attn_l, attn_r, res_w, heads: int, n
     if res_w is not None:
         rst = rst + F.linear(x, res_w).view(x.shape[0], -1, D)
     return rst
+
+
+def rgcn_group_input(x_dict, emb_dict, node_type, local_node_idx, in_channels: int):
+    """RGCN.group_input (mag_pyg/gnn.py:111-124): rows of the homogeneous feature matrix come from the typed feature
+    matrices (x_dict, keyed by node-type int) or the learned embedding tables (emb_dict, keyed by str(node-type int))."""
+    h = torch.zeros(node_type.numel(), in_channels, dtype=next(iter(x_dict.values())).dtype)
+    for key, x in list(x_dict.items()) + [(int(k), e) for k, e in emb_dict.items()]:
+        idx = (node_type == key).nonzero().view(-1)
+        h = h.index_add(0, idx, x[local_node_idx[idx]])
+    return h
+
+
+def rgcn_conv(x, edge_index, edge_type, node_type, rel_w, root_w, root_b):
+    """RGCNConv.forward / .message (mag_pyg/gnn.py:54-68): for every relation, mean over incoming edges of that relation of
+    rel_lins[r](x_j) (transform per edge, then scatter-mean over ALL nodes), plus the per-node-type root Linear."""
+    n = x.shape[0]
+    out = torch.zeros(n, rel_w[0].shape[0], dtype=x.dtype)
+    for r, W in enumerate(rel_w):
+        ei = edge_index[:, edge_type == r]
+        out = out + ops.scatter(F.linear(x[ei[0]], W), ei[1], n, "mean")
+    for t, (W, b) in enumerate(zip(root_w, root_b)):
+        idx = (node_type == t).nonzero().view(-1)
+        out = out.index_add(0, idx, F.linear(x[idx], W, b))
+    return out
+
+
+def rgcn_inference_layer(x_dict, edge_index_dict, key2int, rel_w, root_w, root_b, relu: bool):
+    """One layer of RGCN.inference (mag_pyg/gnn.py:153-169): out[t] = root_lins[t](x_t) + sum over relations into t of
+    rel_lins[r](mean over sources of x_src) — aggregate first (SparseTensor.matmul(reduce='mean')), then transform."""
+    out = {t: F.linear(x, root_w[t], root_b[t]) for t, x in x_dict.items()}
+    for keys, ei in edge_index_dict.items():
+        s, t = key2int[keys[0]], key2int[keys[-1]]
+        agg = ops.scatter(x_dict[s][ei[0]], ei[1], x_dict[t].shape[0], "mean")
+        out[t] = out[t] + F.linear(agg, rel_w[key2int[keys]])
+    return {t: torch.relu(v) if relu else v for t, v in out.items()}

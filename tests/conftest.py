@@ -39,6 +39,11 @@ def golden_gat():
     return torch.load(GOLDEN / "gat_arxiv.pt")
 
 
+@pytest.fixture(scope="session")
+def golden_rgcn():
+    return torch.load(GOLDEN / "rgcn_mag.pt")
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max-norm relative error max|a-b| / max|b| (SURVEY.md §8c parity metric)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

@@ -12,11 +12,16 @@ operators come from oracle/ (the CPU restatement).  What the fixtures therefore 
   * gat_arxiv.pt    — output / gradients of the reference's own DGL `GATConv` class (arxiv_dgl/models.py:95-236) computed
     BY THE REFERENCE FILE on a stand-in `dgl` whose four graph primitives (apply_edges(u_add_v|copy_u), edge_softmax,
     update_all(u_mul_e, sum), in/out_degrees) are restated with plain torch index ops.
+  * rgcn_mag.pt     — the reference's own `RGCNConv` / `RGCN` classes (mag_pyg/gnn.py:26-171): `forward` (per-relation
+    MessagePassing with mean aggregation + per-type root Linear, `group_input` embedding assembly) and `inference`
+    (per-relation SparseTensor.matmul(reduce='mean')) on a small 3-type / 5-relation graph, computed BY THE REFERENCE
+    FILE on restated `MessagePassing.propagate` / `SparseTensor.matmul`.
 Both oracle/ (tests, -m "not gpu") and the CUDA path (tests, -m gpu) must reproduce them.
 """
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import sys
 import types
 from pathlib import Path
@@ -161,6 +166,49 @@ def install_dgl_stubs():
     dgl.utils = mod("dgl.utils", expand_as_pair=lambda x: x if isinstance(x, tuple) else (x, x))
 
 
+class _MessagePassing(torch.nn.Module):
+    """PyG MessagePassing as RGCNConv uses it: x_j = x[edge_index[0]], message(x_j, **extras), aggr over edge_index[1]."""
+
+    def __init__(self, aggr="add"):
+        super().__init__()
+        self.aggr = aggr
+
+    def propagate(self, edge_index, x=None, **kw):
+        msg = self.message(x_j=x[edge_index[0]], **kw)
+        return oo.scatter(msg, edge_index[1], x.size(0), self.aggr)
+
+
+class _SparseTensor:
+    """torch_sparse.SparseTensor(row=, col=) with inferred sizes, .to(), .matmul(x, reduce)."""
+
+    def __init__(self, row, col):
+        self.row, self.col = row, col
+        self.m = int(row.max()) + 1
+
+    def to(self, *a, **k):
+        return self
+
+    def matmul(self, x, reduce="sum"):
+        return oo.scatter(x[self.col], self.row, self.m, reduce)
+
+
+def install_mag_stubs():
+    install_stubs()
+    na = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("stub"))  # noqa: E731
+    sys.modules["torch_sparse"] = types.ModuleType("torch_sparse")
+    sys.modules["torch_sparse"].SparseTensor = _SparseTensor
+    tg = sys.modules["torch_geometric"]
+    tg.utils.to_undirected = na
+    tg.nn.MessagePassing = _MessagePassing
+    tg.data = types.ModuleType("torch_geometric.data")
+    tg.data.Data, tg.data.GraphSAINTRandomWalkSampler = na, na
+    sys.modules["torch_geometric.data"] = tg.data
+    het = types.ModuleType("torch_geometric.utils.hetero")
+    het.group_hetero_graph = na
+    sys.modules["torch_geometric.utils.hetero"] = het
+    tg.utils.hetero = het
+
+
 def small_graph(n=240, e=1400, seed=3):
     from efficient_gnns_b200.synthetic import skewed_edges
     ei = skewed_edges(n, e, seed).numpy()
@@ -272,6 +320,44 @@ def main():
                          d_x=xin.grad.detach().clone(),
                          grads={k: p.grad.detach().clone() for k, p in layer.named_parameters()})
     torch.save(dict(row=torch.from_numpy(rs), col=torch.from_numpy(cs), x=x, layers=gat), OUT / "gat_arxiv.pt")
+    # ---- the reference's RGCN (mag_pyg/gnn.py): forward (MessagePassing formulation) and inference (SparseTensor formulation)
+    install_mag_stubs()
+    sys.path.insert(0, str(REF / "mag_pyg"))
+    spec = importlib.util.spec_from_file_location("mag_gnn", REF / "mag_pyg" / "gnn.py")
+    mag = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mag)
+    gm = torch.Generator().manual_seed(21)
+    nn_t = {0: 60, 1: 50, 2: 20}                              # node type -> count (0 carries features, 1/2 get embeddings)
+    rels = [(1, 2, 90), (2, 1, 90), (1, 0, 200), (0, 1, 200), (0, 0, 240)]   # (src type, dst type, #edges)
+    off = {0: 0, 1: 60, 2: 110}
+    edge_index_dict, key2int, eis, ets = {}, {0: 0, 1: 1, 2: 2}, [], []
+    for i, (sT, dT, e) in enumerate(rels):
+        src = torch.randint(0, nn_t[sT], (e,), generator=gm)
+        dst = torch.randint(0, nn_t[dT], (e,), generator=gm)
+        src[-1], dst[-1] = nn_t[sT] - 1, nn_t[dT] - 1         # upstream infers sizes from the max index: make it exact
+        key = (sT, f"r{i}", dT)
+        edge_index_dict[key] = (src, dst)
+        key2int[key] = i
+        eis.append(torch.stack([src + off[sT], dst + off[dT]]))
+        ets.append(torch.full((e,), i, dtype=torch.long))
+    edge_index, edge_type = torch.cat(eis, 1), torch.cat(ets)
+    node_type = torch.cat([torch.full((nn_t[t],), t, dtype=torch.long) for t in range(3)])
+    local_idx = torch.cat([torch.arange(nn_t[t]) for t in range(3)])
+    x_paper = torch.randn(nn_t[0], 16, generator=gm)
+    torch.manual_seed(4)
+    rg = mag.RGCN(16, 24, 5, 2, 0.5, nn_t, [0], len(rels))
+    rg.eval()                                                 # no dropout: forward and inference must agree
+    out_f = rg({0: x_paper}, edge_index, edge_type, node_type, local_idx)
+    wout = torch.randn(130, 5, generator=gm)
+    (out_f * wout).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in rg.named_parameters()}
+    with torch.no_grad():
+        inf = rg.inference({0: x_paper}, edge_index_dict, key2int)
+    torch.save(dict(num_nodes=nn_t, rels=rels, edge_index_dict={k: torch.stack(v) for k, v in edge_index_dict.items()},
+                    key2int=key2int, edge_index=edge_index, edge_type=edge_type, node_type=node_type,
+                    local_node_idx=local_idx, x_paper=x_paper, state={k: v.detach().clone() for k, v in rg.state_dict().items()},
+                    out_forward=out_f.detach(), out_feat=rg.out_feat.detach(), w=wout, grads=grads,
+                    out_inference={k: v.clone() for k, v in inf.items()}), OUT / "rgcn_mag.pt")
     print("wrote", [p.name for p in OUT.glob("*.pt")])
 
 

@@ -186,6 +186,31 @@ def test_oracle_gat_layer_reproduces_reference_gatconv_fixture(golden_gat, name)
         assert rel_err(t.grad, m["grads"][k]) < 5e-5, k
 
 
+def test_oracle_rgcn_reproduces_reference_rgcn_fixture(golden_rgcn):
+    """oracle.nn.rgcn_* vs the reference's own RGCN class: forward (message-passing form, with gradients) and inference
+    (SparseTensor form)."""
+    G = golden_rgcn
+    st = {k: t.clone().requires_grad_(True) for k, t in G["state"].items()}
+    R, T = len(G["rels"]), 3
+    layer = lambda i: ([st[f"convs.{i}.rel_lins.{r}.weight"] for r in range(R)],
+                       [st[f"convs.{i}.root_lins.{t}.weight"] for t in range(T)],
+                       [st[f"convs.{i}.root_lins.{t}.bias"] for t in range(T)])
+    emb = {"1": st["emb_dict.1"], "2": st["emb_dict.2"]}
+    h = onn.rgcn_group_input({0: G["x_paper"]}, emb, G["node_type"], G["local_node_idx"], 16)
+    h1 = torch.relu(onn.rgcn_conv(h, G["edge_index"], G["edge_type"], G["node_type"], *layer(0)))
+    out = onn.rgcn_conv(h1, G["edge_index"], G["edge_type"], G["node_type"], *layer(1))
+    assert rel_err(h1, G["out_feat"]) < 1e-5 and rel_err(out, G["out_forward"]) < 1e-5
+    (out * G["w"]).sum().backward()
+    for k, t in st.items():
+        assert rel_err(t.grad, G["grads"][k]) < 5e-5, k
+    with torch.no_grad():
+        xd = {0: G["x_paper"], 1: st["emb_dict.1"], 2: st["emb_dict.2"]}
+        xd = onn.rgcn_inference_layer(xd, G["edge_index_dict"], G["key2int"], *layer(0), relu=True)
+        xd = onn.rgcn_inference_layer(xd, G["edge_index_dict"], G["key2int"], *layer(1), relu=False)
+    for t in range(T):
+        assert rel_err(xd[t], G["out_inference"][t]) < 1e-5
+
+
 def test_dgl_graph_conv_and_sign_average_against_dense():
     """oracle.nn.dgl_graph_conv_both / neighbor_average_features vs an explicit dense adjacency."""
     from oracle import nn as onn

@@ -62,6 +62,7 @@ def test_subgraph_and_hetero_match_oracle(shim_path):
     und = to_undirected(ei[:, ei[0] != ei[1]], 50)
     assert np.array_equal(und.numpy(), og.to_undirected(ei[:, ei[0] != ei[1]].numpy(), 50))
     eid = {("a", "r", "b"): torch.tensor([[0, 1], [2, 0]]), ("b", "s", "a"): torch.tensor([[1], [1]])}
-    e, et, nt, li, k2i = group_hetero_graph(eid, {"a": 2, "b": 3})
+    e, et, nt, li, l2g, k2i = group_hetero_graph(eid, {"a": 2, "b": 3})   # the 6-tuple mag_pyg/gnn.py:346-347 unpacks
     assert e.tolist() == [[0, 1, 3], [4, 2, 1]] and et.tolist() == [0, 0, 1] and nt.tolist() == [0, 0, 1, 1, 1]
-    assert li.tolist() == [0, 1, 0, 1, 2] and k2i["b"] == 1
+    assert li.tolist() == [0, 1, 0, 1, 2] and k2i["b"] == 1 and k2i[("b", "s", "a")] == 1
+    assert l2g["a"].tolist() == [0, 1] and l2g["b"].tolist() == [2, 3, 4]
