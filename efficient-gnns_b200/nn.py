@@ -41,8 +41,11 @@ class _LinearTC(torch.autograd.Function):
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            hi, lo = ops.split_tf32(weight, transpose=True)              # B[N=in, K=out]
-            gx = ops.gemm_tf32x3(gy, hi, lo)
+            if gy.shape[1] % 4 == 0:
+                hi, lo = ops.split_tf32(weight, transpose=True)          # B[N=in, K=out]
+                gx = ops.gemm_tf32x3(gy, hi, lo)
+            else:
+                gx = torch.mm(gy, weight)                                # contraction width (out) off the TMA 16-byte pitch
         if ctx.needs_input_grad[1]:
             out_f, in_f = weight.shape
             if ops.wgrad_supported(out_f, in_f):

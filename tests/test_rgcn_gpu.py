@@ -52,7 +52,7 @@ class RelNet(torch.nn.Module):
         return self.convs[1](self.out_feat, edge_index, edge_type, node_type)
 
     def inference(self, x_dict, edge_index_dict, key2int):
-        x_dict = dict(x_dict, **{int(k): e for k, e in self.emb_dict.items()})
+        x_dict = {**x_dict, **{int(k): e for k, e in self.emb_dict.items()}}
         adjs = {k: SparseTensor(row=ei[1], col=ei[0], sparse_sizes=(x_dict[key2int[k[-1]]].size(0), x_dict[key2int[k[0]]].size(0)))
                 for k, ei in edge_index_dict.items()}
         for i, conv in enumerate(self.convs):
