@@ -44,6 +44,11 @@ def golden_rgcn():
     return torch.load(GOLDEN / "rgcn_mag.pt")
 
 
+@pytest.fixture(scope="session")
+def golden_sign():
+    return torch.load(GOLDEN / "sign_arxiv.pt")
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max-norm relative error max|a-b| / max|b| (SURVEY.md §8c parity metric)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

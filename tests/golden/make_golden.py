@@ -12,11 +12,15 @@ operators come from oracle/ (the CPU restatement).  What the fixtures therefore 
   * gat_arxiv.pt    — output / gradients of the reference's own DGL `GATConv` class (arxiv_dgl/models.py:95-236) computed
     BY THE REFERENCE FILE on a stand-in `dgl` whose four graph primitives (apply_edges(u_add_v|copy_u), edge_softmax,
     update_all(u_mul_e, sum), in/out_degrees) are restated with plain torch index ops.
+  * sign_arxiv.pt   — `neighbor_average_features` of arxiv_dgl/sign.py:175-201 (R chained mean aggregations) run BY THE
+    REFERENCE FILE on the same `dgl` stand-in, on the directed graph (zero in-degree rows included).
   * rgcn_mag.pt     — the reference's own `RGCNConv` / `RGCN` classes (mag_pyg/gnn.py:26-171): `forward` (per-relation
     MessagePassing with mean aggregation + per-type root Linear, `group_input` embedding assembly) and `inference`
     (per-relation SparseTensor.matmul(reduce='mean')) on a small 3-type / 5-relation graph, computed BY THE REFERENCE
     FILE on restated `MessagePassing.propagate` / `SparseTensor.matmul`.
 Both oracle/ (tests, -m "not gpu") and the CUDA path (tests, -m gpu) must reproduce them.
+Regenerating is deterministic up to the summation order of torch's multi-threaded CPU index_add_/scatter_add_ backward
+(differences at the 1e-7 level in a few gradient entries), far inside the tolerances the tests apply.
 """
 from __future__ import annotations
 
@@ -142,6 +146,10 @@ class _DGLGraph:
             raise NotImplementedError(f)
 
     def update_all(self, msg, red):
+        if msg[0] == "copy_u" and red[0] == "mean":          # sign.py:182-183 (mean over in-edges, zero if none)
+            assert msg[2] == red[1]
+            self.dstdata[red[2]] = oo.scatter(self.srcdata[msg[1]][self.src], self.dst, self.n, "mean")
+            return
         assert msg[0] == "u_mul_e" and red[0] == "sum" and msg[3] == red[1]
         m = self.srcdata[msg[1]][self.src] * self.edata[msg[2]]
         self.dstdata[red[2]] = torch.zeros((self.n,) + tuple(m.shape[1:]), dtype=m.dtype).index_add_(0, self.dst, m)
@@ -156,7 +164,8 @@ def install_dgl_stubs():
 
     dgl = mod("dgl")
     dgl.function = mod("dgl.function", u_add_v=lambda a, b, o: ("u_add_v", a, b, o), copy_u=lambda u, o: ("copy_u", u, o),
-                       u_mul_e=lambda u, e, o: ("u_mul_e", u, e, o), sum=lambda m, o: ("sum", m, o))
+                       u_mul_e=lambda u, e, o: ("u_mul_e", u, e, o), sum=lambda m, o: ("sum", m, o),
+                       mean=lambda m, o: ("mean", m, o))
     dgl.nn = mod("dgl.nn")
     dgl.nn.pytorch = mod("dgl.nn.pytorch", GraphConv=None)
     dgl.nn.pytorch.utils = mod("dgl.nn.pytorch.utils", Identity=torch.nn.Identity)
@@ -320,6 +329,24 @@ def main():
                          d_x=xin.grad.detach().clone(),
                          grads={k: p.grad.detach().clone() for k, p in layer.named_parameters()})
     torch.save(dict(row=torch.from_numpy(rs), col=torch.from_numpy(cs), x=x, layers=gat), OUT / "gat_arxiv.pt")
+    # ---- SIGN precompute: the reference's neighbor_average_features (arxiv_dgl/sign.py:175-201)
+    ogbm = sys.modules["ogb.nodeproppred"]
+    ogbm.DglNodePropPredDataset = None
+    if "torch.utils.tensorboard" not in sys.modules:
+        try:
+            importlib.import_module("torch.utils.tensorboard")
+        except Exception:                                    # tensorboard is not installed everywhere: sign.py only names it
+            tb = types.ModuleType("torch.utils.tensorboard")
+            tb.SummaryWriter = None
+            sys.modules["torch.utils.tensorboard"] = tb
+    sign = importlib.import_module("sign")
+    row_d, col_d, _ = og.to_sparse_adj_t(ei, n)              # directed: row = destination, col = source
+    gd = _DGLGraph(torch.from_numpy(col_d), torch.from_numpy(row_d), n)
+    gd.ndata["feat"] = x
+    hops = sign.neighbor_average_features(gd, types.SimpleNamespace(R=3, dataset="ogbn-arxiv"))
+    torch.save(dict(row=torch.from_numpy(row_d), col=torch.from_numpy(col_d), x=x, hops=[h.clone() for h in hops]),
+               OUT / "sign_arxiv.pt")
+
     # ---- the reference's RGCN (mag_pyg/gnn.py): forward (MessagePassing formulation) and inference (SparseTensor formulation)
     install_mag_stubs()
     sys.path.insert(0, str(REF / "mag_pyg"))

@@ -211,6 +211,17 @@ def test_oracle_rgcn_reproduces_reference_rgcn_fixture(golden_rgcn):
         assert rel_err(xd[t], G["out_inference"][t]) < 1e-5
 
 
+def test_oracle_sign_average_reproduces_reference_function_fixture(golden_sign):
+    """oracle.nn.neighbor_average_features vs the reference's own function (arxiv_dgl/sign.py:175-201)."""
+    G = golden_sign
+    n = G["x"].shape[0]
+    hops = onn.neighbor_average_features(G["x"], G["row"], G["col"], n, 3)
+    assert len(hops) == len(G["hops"]) == 4
+    for a, b in zip(hops, G["hops"]):
+        assert rel_err(a, b) < 1e-6
+    assert (torch.bincount(G["row"], minlength=n) == 0).any()      # the fixture exercises zero in-degree rows
+
+
 def test_dgl_graph_conv_and_sign_average_against_dense():
     """oracle.nn.dgl_graph_conv_both / neighbor_average_features vs an explicit dense adjacency."""
     from oracle import nn as onn
