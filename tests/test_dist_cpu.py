@@ -88,3 +88,32 @@ def test_plan_properties():
             assert (blk[:k] >= 0).all() and (blk[k:] < 0).all()
         loads = [int(rc[plan.perm[r * plan.block:r * plan.block + plan.real_rows(r)]].sum()) for r in range(world)]
         assert max(loads) - min(loads) <= 100
+
+
+@pytest.mark.parametrize("world", [3, 4, 8])
+def test_all_ranks_simulated_in_one_process_match_full_oracle(world):
+    """The same shard/gather/aggregate pipeline as the gloo test, with every rank's part computed in this process:
+    covers the world sizes the scaling run uses (padding rows appear when world does not divide N)."""
+    n, e, K = 1003, 7000, 8
+    ei = skewed_edges(n, e, 1).numpy()
+    row, col, _ = og.to_sparse_adj_t(ei, n)
+    r, c = og.to_symmetric(row, col, n)
+    r, c, v = map(torch.from_numpy, og.gcn_norm(r, c, n))
+    adj = SparseTensor(row=r, col=c, value=v, sparse_sizes=(n, n), is_sorted=True)
+    plan = D.make_plan(adj.storage.rowcount(), world)
+    rel = D.relabel_adjacency(adj, plan)
+    h = torch.randn(n, K, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    full = D.scatter_rows(h, plan)                       # what the all-gather of every rank's block assembles
+    y_pad = torch.zeros(plan.n_pad, K, dtype=torch.float64)
+    nnz = []
+    for rank in range(world):
+        rowptr, colx, val = D.shard_rows(rel, plan, rank)
+        r0, r1 = plan.rows_of(rank)
+        assert rowptr.numel() == plan.real_rows(rank) + 1 and r1 - r0 == plan.real_rows(rank) <= plan.block
+        y_pad[r0:r1] = oo.spmm_csr(rowptr, colx, val.double(), full, plan.real_rows(rank), "sum")
+        nnz.append(int(colx.numel()))
+    ref = oo.spmm_scatter(r, c, v.double(), h, n, "sum")
+    assert (y_pad[plan.inv] - ref).abs().max().item() < 1e-12 * max(1.0, ref.abs().max().item())
+    assert sum(nnz) == r.numel() and max(nnz) <= 1.25 * sum(nnz) / world    # degree-balanced (one hub dominates at this size)
+    pad_rows = torch.ones(plan.n_pad, dtype=torch.bool); pad_rows[plan.inv] = False
+    assert int(pad_rows.sum()) == plan.n_pad - n and torch.all(full[pad_rows] == 0)
