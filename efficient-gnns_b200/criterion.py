@@ -1,4 +1,5 @@
-"""Drop-in for the reference's ``criterion.py`` (arxiv_pyg/criterion.py:8-149; same copies in mag_pyg/, ppi_pyg/).
+"""Drop-in for the reference's ``criterion.py`` (arxiv_pyg/criterion.py:8-149 and the identical mag_pyg/ copy; the PPI
+variant with binary cross-entropy is ``criterion_ppi.py``).
 
 Same function names, argument order and return convention ``(loss, loss_cls, loss_aux)``; every loss is computed
 by b200gnn kernels (fused row losses, edge-list passes, tcgen05 3xTF32 GEMMs for the S x S contractions) and is
@@ -56,6 +57,32 @@ class _RowLoss(torch.autograd.Function):
 
 def cross_entropy(logits, labels):
     return _RowLoss.apply(logits, labels, None, 0.0, 1.0)[0]
+
+
+class _BCE(torch.autograd.Function):
+    """F.binary_cross_entropy_with_logits(z, target) (mean over all elements); target_is_logits => sigmoid(target)."""
+
+    @staticmethod
+    def forward(ctx, z, target, target_is_logits: bool):
+        z, target = z.contiguous(), target.contiguous().to(torch.float32)
+        n = z.numel()
+        loss, d_z = _new(1, like=z), torch.empty_like(z)
+        part = _new(int(_L().b200gnn_reduce_slots(n)), like=z)
+        lib.check(_L().b200gnn_bce_logits_fwd_bwd_f32(_f32(z, "z"), _f32(target, "target"), int(target_is_logits), n, 1.0,
+                                                     _f32(d_z, "d_z"), _f32(loss, "loss"), _f32(part, "partial"),
+                                                     lib.stream_ptr()), "bce_logits_fwd_bwd_f32")
+        ctx.save_for_backward(d_z)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_z,) = ctx.saved_tensors
+        return d_z * g, None, None
+
+
+def bce_with_logits(logits, labels):
+    """ppi_pyg/criterion.py:11 — multi-label classification loss of the PPI student."""
+    return _BCE.apply(logits, labels, False)
 
 
 def kd_criterion(logits, labels, teacher_logits, alpha=0.9, T=4):
@@ -143,9 +170,9 @@ class _NormalizedMSE(torch.autograd.Function):
         return da, db
 
 
-def fitnet_criterion(logits, labels, feat, teacher_feat, beta=1000):
+def fitnet_criterion(logits, labels, feat, teacher_feat, beta=1000, _cls=None):
     """criterion.py:24-36."""
-    loss_cls = cross_entropy(logits, labels)
+    loss_cls = (_cls or cross_entropy)(logits, labels)
     loss_aux = _NormalizedMSE.apply(feat, teacher_feat)
     return loss_cls + beta * loss_aux, loss_cls, loss_aux
 
@@ -184,9 +211,9 @@ class _AttentionMSE(torch.autograd.Function):
         return tuple(out)
 
 
-def at_criterion(logits, labels, feat, teacher_feat, beta=1000):
+def at_criterion(logits, labels, feat, teacher_feat, beta=1000, _cls=None):
     """criterion.py:39-54."""
-    loss_cls = cross_entropy(logits, labels)
+    loss_cls = (_cls or cross_entropy)(logits, labels)
     loss_aux = _AttentionMSE.apply(feat, teacher_feat)
     return loss_cls + beta * loss_aux, loss_cls, loss_aux
 
@@ -245,11 +272,11 @@ class _GSP(torch.autograd.Function):
         return out[0], out[1], None
 
 
-def gpw_criterion(logits, labels, feat, teacher_feat, kernel='cosine', beta=1, max_samples=8192, sampled_inds=None):
+def gpw_criterion(logits, labels, feat, teacher_feat, kernel='cosine', beta=1, max_samples=8192, sampled_inds=None, _cls=None):
     """criterion.py:57-92."""
     if kernel not in _KERNELS:
         raise NotImplementedError
-    loss_cls = cross_entropy(logits, labels)
+    loss_cls = (_cls or cross_entropy)(logits, labels)
     inds = _sample(feat.shape[0], max_samples, feat.device, sampled_inds)
     if inds is not None:
         feat, teacher_feat = feat[inds], teacher_feat[inds]
@@ -276,11 +303,14 @@ class LspPlan:
         rowptr = torch.zeros(self.n_seg + 1, dtype=torch.long, device=dst.device)
         torch.cumsum(counts, 0, out=rowptr[1:])
         self.rowptr = rowptr.to(torch.int32).contiguous()
+        self.edge_index = edge_index          # keeps the keyed storage alive: its address cannot be recycled while cached
 
     @classmethod
     def of(cls, edge_index: torch.Tensor) -> "LspPlan":
         key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device))
         plan = cls._cache.get(key)
+        if plan is not None and plan.edge_index.data_ptr() != edge_index.data_ptr():
+            plan = None
         if plan is None:
             if len(cls._cache) > 8:
                 cls._cache.clear()
@@ -318,11 +348,11 @@ class _LSP(torch.autograd.Function):
         return d * gout, None, None, None, None
 
 
-def lpw_criterion(logits, labels, feat, teacher_feat, edge_index, kernel='cosine', beta=100, criterion='kld'):
+def lpw_criterion(logits, labels, feat, teacher_feat, edge_index, kernel='cosine', beta=100, criterion='kld', _cls=None):
     """criterion.py:95-126 (teacher features are constants of the loss, as in the reference's call sites)."""
     if kernel not in _KERNELS or criterion not in ("kld", "mse"):
         raise NotImplementedError
-    loss_cls = cross_entropy(logits, labels)
+    loss_cls = (_cls or cross_entropy)(logits, labels)
     plan = LspPlan.of(edge_index)
     loss_aux = _LSP.apply(feat, teacher_feat.detach(), plan, _KERNELS[kernel], 0 if criterion == "kld" else 1)
     return loss_cls + beta * loss_aux, loss_cls, loss_aux
@@ -361,9 +391,9 @@ class _NCE(torch.autograd.Function):
         return d_fs, d_ft, None
 
 
-def nce_criterion(logits, labels, feat, teacher_feat, beta=0.5, nce_T=0.075, max_samples=8192, sampled_inds=None):
+def nce_criterion(logits, labels, feat, teacher_feat, beta=0.5, nce_T=0.075, max_samples=8192, sampled_inds=None, _cls=None):
     """criterion.py:129-149."""
-    loss_cls = cross_entropy(logits, labels)
+    loss_cls = (_cls or cross_entropy)(logits, labels)
     inds = _sample(feat.shape[0], max_samples, feat.device, sampled_inds)
     if inds is not None:
         feat, teacher_feat = feat[inds], teacher_feat[inds]

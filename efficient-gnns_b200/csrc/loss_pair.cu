@@ -209,6 +209,31 @@ __global__ void __launch_bounds__(256) row_axpy_kernel(const float* __restrict__
     y[i] = fmaf(alpha * coef[i / F], x[i], y[i]);
 }
 
+// F.binary_cross_entropy_with_logits(z, t) (ppi_pyg/criterion.py:11,13): element loss max(z,0) - z t + log1p(exp(-|z|)),
+// mean over all elements; d z = (sigmoid(z) - t) * w.  target_is_logits: t = sigmoid(target) (the teacher term of :13).
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ z, const float* __restrict__ target,
+                                                         int target_is_logits, int64_t n, float w, float* __restrict__ dz,
+                                                         float* __restrict__ partial) {
+  __shared__ float s_red[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = z[i];
+    float t = target[i];
+    if (target_is_logits) t = 1.f / (1.f + expf(-t));
+    acc += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+    if (dz) dz[i] = (1.f / (1.f + expf(-x)) - t) * w;
+  }
+  acc = warp_sum_f(acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_red[k];
+    partial[blockIdx.x] = t;
+  }
+}
+
 static inline int ew_grid(int64_t n, int per = 256 * 4) {
   int64_t g = (n + per - 1) / per;
   if (g > 148 * 8) g = 148 * 8;
@@ -245,6 +270,19 @@ extern "C" int b200gnn_mse_fwd_bwd_f32(const float* a, const float* b, int64_t n
   const int grid = ew_grid(n);
   int rc;
   mse_fwd_bwd_kernel<<<grid, 256, 0, st>>>(a, b, n, grad_weight * 2.f / (float)n, d_a, partial);
+  if ((rc = check_launch())) return rc;
+  sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, 1.0 / (double)n, loss_out);
+  return check_launch();
+}
+
+// loss_out[0] = mean BCE-with-logits; d_z (nullable) = grad_weight * (sigmoid(z) - t) / n
+extern "C" int b200gnn_bce_logits_fwd_bwd_f32(const float* z, const float* target, int target_is_logits, int64_t n,
+                                              float grad_weight, float* d_z, float* loss_out, float* partial, void* stream) {
+  if (!z || !target || !loss_out || !partial || n <= 0) return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(n);
+  int rc;
+  bce_logits_kernel<<<grid, 256, 0, st>>>(z, target, target_is_logits, n, grad_weight / (float)n, d_z, partial);
   if ((rc = check_launch())) return rc;
   sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, 1.0 / (double)n, loss_out);
   return check_launch();

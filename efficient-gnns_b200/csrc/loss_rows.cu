@@ -10,7 +10,7 @@ namespace b200gnn {
 
 constexpr int LOSS_THREADS = 256;
 constexpr int LOSS_WARPS = LOSS_THREADS / 32;
-constexpr int LOSS_MAX_PER_LANE = 8;  // C <= 256
+constexpr int LOSS_MAX_C = 1024;      // classes per row: NJ = ceil(C/32) values per lane, NJ in {2, 8, 16, 32}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -24,6 +24,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // partial[cta][2] = {sum_i CE_i, sum_i KL_i}
+template <int LOSS_MAX_PER_LANE>
 __global__ void __launch_bounds__(LOSS_THREADS) kd_rows_kernel(
     const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ train_idx, int64_t n_train,
     const int64_t* __restrict__ labels, const float* __restrict__ teacher, int64_t ldt, int C, float inv_T,
@@ -125,7 +126,7 @@ extern "C" int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld, cons
                                            float* loss_out, float* partial, void* stream) {
   if (!logits || !labels || !dlogits || !loss_out || !partial || n_train < 0 || C <= 0 || ld < C || ldd < C)
     return B200GNN_ERR_BAD_ARG;
-  if (C > 32 * LOSS_MAX_PER_LANE) return B200GNN_ERR_UNSUPPORTED;
+  if (C > LOSS_MAX_C) return B200GNN_ERR_UNSUPPORTED;
   if (teacher_logits && (ldt < C || T <= 0.f)) return B200GNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)b200gnn_kd_partials(n_train);
@@ -134,8 +135,14 @@ extern "C" int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld, cons
   const float w_cls = (kd ? (1.f - alpha) : 1.f) / (float)n_norm;
   const float w_kd = kd ? alpha * T * T / ((float)n_norm * (float)C) : 0.f;
   int rc;
-  kd_rows_kernel<<<grid, LOSS_THREADS, 0, st>>>(logits, ld, train_idx, n_train, labels, teacher_logits, ldt, (int)C,
-                                                kd ? 1.f / T : 1.f, w_cls, w_kd, dlogits, ldd, partial);
+#define B200GNN_KD_LAUNCH(NJ)                                                                                     \
+  kd_rows_kernel<NJ><<<grid, LOSS_THREADS, 0, st>>>(logits, ld, train_idx, n_train, labels, teacher_logits, ldt, \
+                                                    (int)C, kd ? 1.f / T : 1.f, w_cls, w_kd, dlogits, ldd, partial)
+  if (C <= 64) B200GNN_KD_LAUNCH(2);            // ogbn-arxiv: 40 classes
+  else if (C <= 256) B200GNN_KD_LAUNCH(8);
+  else if (C <= 512) B200GNN_KD_LAUNCH(16);     // ogbn-mag: 349 classes (mag_pyg/gnn.py:399)
+  else B200GNN_KD_LAUNCH(32);
+#undef B200GNN_KD_LAUNCH
   if ((rc = check_launch())) return rc;
   kd_finalize_kernel<<<1, 256, 0, st>>>(partial, grid, 1.f / (float)n_norm, 1.f / ((float)n_norm * (float)C), alpha, T,
                                       kd ? 1 : 0, loss_out);

@@ -127,11 +127,12 @@ def run(args):
         line = {"metric": B.METRIC, "value": 6 * nnz / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": B.workload_config(ds, nnz, {
+                "config": B.workload_config(ds, nnz),
+                "engine": {
                     "parallelism": f"node-parallel x{world}: degree-balanced row blocks, one NCCL all-gather per aggregation",
                     "cuda_graph": bool(graph), "exchange_bytes_received_per_rank_per_step": ex,
                     "nvlink_floor_ms": ex / 770e9 * 1e3,
-                    "aggregations_executed": tr.aggregations_per_step()}),
+                    "aggregations_executed": tr.aggregations_per_step()},
                 "roofline": {"bound": "nvlink+hbm", "note": "multi-GPU point: the all-gathers bound the step; see "
                              "nvlink_floor_ms (bytes received per rank / 770 GB/s measured peer bandwidth)",
                              "achieved": ex / (ms_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",

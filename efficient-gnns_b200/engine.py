@@ -192,6 +192,14 @@ class GCNStudentTrainer:
                 self.running_mean[l].copy_(sd[f"bns.{l}.running_mean"]); self.running_var[l].copy_(sd[f"bns.{l}.running_var"])
 
     # ------------------------------------------------------------------ forward / backward
+    def activation_pattern(self, l: int) -> torch.Tensor:
+        """bool [N, dims[l+1]]: ReLU-active AND kept by dropout in the last training forward of hidden layer l."""
+        return self.A[l] > 0
+
+    def out_feat(self) -> torch.Tensor:
+        """The reference's ``model.out_feat`` (arxiv_pyg/gnn.py:51): output of the last hidden layer."""
+        return self.A[-1]
+
     def dropout_offset(self, layer: int, step: int) -> int:
         return layer + step * self.L
 

@@ -6,6 +6,7 @@ raises; nothing in this package falls back to PyTorch or CPU arithmetic.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
@@ -67,6 +68,7 @@ SIGNATURES = {
     "b200gnn_row_normalize_bwd_f32": (_int, [_f32p, _f32p, _f32p, _i64, _i64, _f32, _f32, _f32p, _int, _ptr]),
     "b200gnn_reduce_slots": (_i64, [_i64]),
     "b200gnn_mse_fwd_bwd_f32": (_int, [_f32p, _f32p, _i64, _f32, _f32p, _f32p, _f32p, _ptr]),
+    "b200gnn_bce_logits_fwd_bwd_f32": (_int, [_f32p, _f32p, _int, _i64, _f32, _f32p, _f32p, _f32p, _ptr]),
     "b200gnn_row_sqnorm_f32": (_int, [_f32p, _i64, _i64, _f32p, _ptr]),
     "b200gnn_row_sqnorm_bwd_f32": (_int, [_f32p, _f32p, _i64, _i64, _f32p, _ptr]),
     "b200gnn_nce_rows_f32": (_int, [_f32p, _i64, _f32p, _f32p, _ptr]),
@@ -109,6 +111,10 @@ def load() -> C.CDLL:
     if lib.b200gnn_abi_version() != 1:
         raise B200GnnError("libb200gnn.so ABI version mismatch; rebuild")
     _lib = lib
+    report = os.environ.get("B200GNN_LAUNCH_REPORT")
+    if report:          # evidence for out-of-process runs (the unmodified reference scripts on the shims): kernels launched
+        import atexit
+        atexit.register(lambda: Path(report).write_text(str(int(lib.b200gnn_launch_count()))))
     return lib
 
 

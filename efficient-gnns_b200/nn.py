@@ -59,6 +59,8 @@ class _LinearTC(torch.autograd.Function):
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.linear on the b200gnn GEMMs when the layout allows (feature widths multiples of 4), cuBLAS otherwise."""
+    if x.dim() == 2 and x.shape[0] == 0:          # an empty node-type mask / relation (mag_pyg/gnn.py:61-66): F.linear semantics
+        return torch.nn.functional.linear(x, weight, bias)
     if x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and x.dtype == torch.float32:
         return _LinearTC.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
@@ -143,6 +145,35 @@ class SAGEConv(torch.nn.Module):
 
     def __repr__(self):
         return f"SAGEConv({self.in_channels}, {self.out_channels})"
+
+
+class GINConv(torch.nn.Module):
+    """out = nn((1 + eps) * x_i + sum_j x_j)  (PyG GINConv; BASELINE.json north_star names it beside GCN/SAGE — the
+    reference's mol_pyg/ students — and it is the sum-aggregation SpMM followed by the caller's MLP)."""
+
+    def __init__(self, nn: torch.nn.Module, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = float(eps)
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.tensor([float(eps)]))
+        else:
+            self.register_buffer("eps", torch.tensor([float(eps)]))
+
+    def reset_parameters(self):
+        for m in self.nn.modules():
+            if m is not self.nn and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+        self.eps.data.fill_(self.initial_eps)
+
+    def forward(self, x, edge_index):
+        adj = _as_adj(edge_index, x.size(0))
+        if adj.has_value():
+            adj = adj.set_value(None)
+        return self.nn(ops.matmul(adj, x, "sum") + (1.0 + self.eps) * x)
+
+    def __repr__(self):
+        return f"GINConv(nn={self.nn})"
 
 
 class DGLGraphConv(torch.nn.Module):
@@ -234,6 +265,8 @@ class MessagePassing(torch.nn.Module):
             src, dst = edge_index[0], edge_index[1]
             n = x.size(0) if x is not None else int(dst.max()) + 1
         params = inspect.signature(self.message).parameters
+        if dst.numel() == 0 and x is not None:        # empty relation: nothing to gather, message() never sees an empty batch
+            return self.update(x.new_zeros(n, self._empty_out_width(x, kwargs)))
         args = {}
         for name in params:
             if name.endswith("_j"):
@@ -249,6 +282,17 @@ class MessagePassing(torch.nn.Module):
 
     def message(self, x_j):
         return x_j
+
+    def _empty_out_width(self, x, kwargs) -> int:
+        """Output width of message() for an empty edge set, probed with a zero-row batch on the CPU-free meta path."""
+        params = inspect.signature(self.message).parameters
+        args = {}
+        for name in params:
+            if name.endswith("_j") or name.endswith("_i"):
+                args[name] = kwargs[name[:-2]][:0]
+            elif name in kwargs:
+                args[name] = kwargs[name]
+        return int(self.message(**args).shape[1])
 
     def update(self, inputs):
         return inputs

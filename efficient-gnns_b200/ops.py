@@ -31,8 +31,9 @@ def spmm_csr(g: CsrGraph, x: torch.Tensor, reduce: str = "sum", bias: Optional[t
         raise ValueError(f"reduce={reduce!r}: the engine implements sum/add/mean (what the reference path uses)")
     if x.dim() != 2:
         raise lib.B200GnnError("spmm: dense operand must be [n_src, K]")
-    if x.shape[0] != g.n_cols:
-        raise lib.B200GnnError(f"spmm: dense operand has {x.shape[0]} rows, matrix has {g.n_cols} columns")
+    if x.shape[0] < g.n_cols:   # extra trailing rows are harmless (upstream accepts them: mag_pyg/gnn.py:151-162 infers
+        raise lib.B200GnnError(  # the sparse sizes as max+1 and multiplies by the full per-type feature matrix)
+            f"spmm: dense operand has {x.shape[0]} rows, matrix has {g.n_cols} columns")
     K = x.shape[1]
     if out is None:
         out = torch.empty(g.n_rows, K, dtype=torch.float32, device=x.device)
@@ -66,7 +67,10 @@ class _SpMM(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         st = ctx.adj.storage
-        gt = st.engine_csc("mean" if ctx.reduce == "mean" else "value")
+        if ctx.reduce == "mean":
+            gt = st.engine_csc("mean" if st.value() is None else "mean_value")
+        else:
+            gt = st.engine_csc("value")
         return spmm_csr(gt, grad_out.contiguous(), "sum"), None, None
 
 

@@ -1,1 +1,1 @@
-from efficient_gnns_b200.nn import GCNConv, SAGEConv, GATConv, MessagePassing  # noqa: F401
+from efficient_gnns_b200.nn import GCNConv, SAGEConv, GATConv, GINConv, MessagePassing  # noqa: F401

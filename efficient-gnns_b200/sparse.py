@@ -187,7 +187,8 @@ class SparseStorage:
 
     def engine_csc(self, mode: str) -> CsrGraph:
         """Transpose as CSR, for the SpMM backward (upstream: colptr, row[csr2csc], value[csr2csc]).
-        mode 'value': carries value[csr2csc] (None if unweighted); 'mean': weights 1/max(rowcount[row],1)."""
+        mode 'value': carries value[csr2csc] (None if unweighted); 'mean': weights 1/max(rowcount[row],1);
+        'mean_value': value[csr2csc]/max(rowcount[row],1) (mean of a WEIGHTED matrix: forward is sum(val*x)/rowcount)."""
         key = "csc_" + mode
         g = self._engine.get(key)
         if g is None:
@@ -197,6 +198,8 @@ class SparseStorage:
                 val = None if self._value is None else self._value[perm]
             elif mode == "mean":
                 val = (1.0 / self.rowcount().clamp(min=1).to(torch.float32))[row_t]
+            elif mode == "mean_value":
+                val = self._value[perm].to(torch.float32) / self.rowcount().clamp(min=1).to(torch.float32)[row_t]
             else:
                 raise ValueError(mode)
             g = csr_graph_from(self.colptr(), row_t, val, self._sizes[1], self._sizes[0])

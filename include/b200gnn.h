@@ -208,7 +208,7 @@ int b200gnn_adam_step_f32(float* params, const float* grads, float* exp_avg,
  * zeroes the other rows.  loss_out[3] = {loss, loss_cls, loss_kd}.
  * n_norm: row count the means are taken over (0 => n_train; node-parallel
  * shards pass the GLOBAL number of training rows and sum loss_out across ranks).
- * partial: float[2*b200gnn_kd_partials(n_train)] scratch.  C <= 256.
+ * partial: float[2*b200gnn_kd_partials(n_train)] scratch.  C <= 1024 (ogbn-mag: 349).
  * ------------------------------------------------------------------ */
 int64_t b200gnn_kd_partials(int64_t n_train);
 int b200gnn_kd_loss_fwd_bwd_f32(const float* logits, int64_t ld,
@@ -266,6 +266,12 @@ int64_t b200gnn_reduce_slots(int64_t n);
 int b200gnn_mse_fwd_bwd_f32(const float* a, const float* b, int64_t n,
                             float grad_weight, float* d_a, float* loss_out,
                             float* partial, void* stream);
+/* F.binary_cross_entropy_with_logits(z, target) over n elements (ppi_pyg/criterion.py:11; target_is_logits != 0:
+ * target = sigmoid(target), the teacher term of :13).  d_z (nullable) = grad_weight * (sigmoid(z) - t) / n */
+int b200gnn_bce_logits_fwd_bwd_f32(const float* z, const float* target,
+                                   int target_is_logits, int64_t n,
+                                   float grad_weight, float* d_z, float* loss_out,
+                                   float* partial, void* stream);
 /* feat.pow(2).sum(-1)  (at_criterion :44-45) and its backward */
 int b200gnn_row_sqnorm_f32(const float* x, int64_t n, int64_t F, float* out, void* stream);
 int b200gnn_row_sqnorm_bwd_f32(const float* x, const float* d_out, int64_t n,

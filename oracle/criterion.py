@@ -141,3 +141,19 @@ def nce_criterion(logits, labels, feat, teacher_feat, beta: float = 0.5, nce_T: 
     ls = _log_softmax(z)
     loss_aux = -ls.diagonal().mean()
     return loss_cls + beta * loss_aux, loss_cls, loss_aux
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ppi_pyg/criterion.py — the multi-label variant: the classification term is binary cross-entropy with logits and
+# kd_criterion distils through sigmoid(teacher_logits) (:8-19); the auxiliary terms are the ones above.
+def bce_with_logits(logits, targets):
+    """F.binary_cross_entropy_with_logits, mean over all elements: max(z,0) - z t + log(1 + exp(-|z|))."""
+    z = logits
+    return (z.clamp_min(0) - z * targets + torch.log1p(torch.exp(-z.abs()))).mean()
+
+
+def kd_criterion_ppi(logits, labels, teacher_logits, alpha: float = 0.5, T: float = 1):
+    """ppi_pyg/criterion.py:8-19."""
+    loss_cls = bce_with_logits(logits, labels)
+    loss_kd = bce_with_logits(logits, torch.sigmoid(teacher_logits))
+    return loss_kd * (alpha * T * T) + loss_cls * (1 - alpha), loss_cls, loss_kd

@@ -24,7 +24,8 @@ def test_reference_arm_prints_exactly_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["scatter_add_value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["scaling"] == "strong"
+    assert set(d["config"]) == {"workload", "edges_per_step", "nnz_walked", "l2_policy"}       # the same keys as the GPU arm
 
 
 def test_reference_arm_is_silent_on_non_zero_ranks():

@@ -1,0 +1,66 @@
+"""BASELINE.json configs[1] at its REAL size (N=169,343, nnz(Â)=2.5 M, 128-256-256-40) against the fp64 CPU restatement:
+the same comparison bench.py prints as ``parity_check``.
+
+Bars: logits / hidden / losses <= 1e-5 max-norm relative against the free-running oracle; every gradient
+<= 1e-5 max-norm AND Frobenius once the engine's activation pattern is imposed on the oracle (arithmetic error only);
+the pattern itself may differ from sign(pre-activation) only where |pre| is within 1e-5 of zero (rounding distance),
+and the number of such flips is reported.  Against the free-running oracle the gradients are compared in the
+Frobenius norm with the bound that the measured flip count explains."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+
+import efficient_gnns_b200  # noqa: F401
+from efficient_gnns_b200 import ops, sparse, synthetic
+from efficient_gnns_b200.engine import GCNStudentTrainer
+from oracle import check, graph as og
+
+pytestmark = pytest.mark.gpu
+DIMS = [128, 256, 256, 40]
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def arxiv():
+    ds = synthetic.make_node_dataset(synthetic.ARXIV, seed=0)
+    n = ds.num_nodes
+    row, col, _ = og.to_sparse_adj_t(ds.edge_index.numpy(), n)
+    r, c = og.to_symmetric(row, col, n)
+    rn, cn, vn = og.gcn_norm(r, c, n)
+    csr = (torch.from_numpy(og.ind2ptr(rn, n)), torch.from_numpy(cn), torch.from_numpy(vn))
+    return ds, (r, c), csr
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_configs1_full_size_step_matches_fp64_oracle(arxiv, p):
+    ds, (r, c), (ptr, col, val) = arxiv
+    n = ds.num_nodes
+    adj = sparse.SparseTensor(row=torch.from_numpy(r).cuda(), col=torch.from_numpy(c).cuda(), sparse_sizes=(n, n),
+                              is_sorted=True)
+    tr = GCNStudentTrainer(adj, DIMS, dropout=p, lr=0.01, seed=0)
+    assert tr.nnz == col.numel()
+    state = {k: v.cpu() for k, v in tr.state_dict().items()}
+    masks = None
+    if p > 0:
+        masks = [ops.dropout_mask(n, DIMS[l + 1], p, tr.seed, tr.dropout_offset(l, 0)).cpu().bool() for l in range(2)]
+    x, y, t, idx = ds.x, ds.y.squeeze(1), ds.teacher_logits, ds.split_idx["train"]
+    tr.train_step(x.cuda(), y.cuda(), idx.cuda(), t.cuda())
+    torch.cuda.synchronize()
+    res = check.compare_engine_step(tr, x, y, t, idx, ptr, col, val.double(), masks, state)
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / f"fullscale_parity_p{int(p * 100)}.json").write_text(json.dumps(res, indent=1))
+    free, pat = res["free"], res["pattern"]
+    # forward quantities and losses: free-running oracle
+    assert free["logits_max"] <= 1e-5 and free["hidden_max"] <= 1e-5, free
+    assert max(free["loss_rel"]) <= 1e-5, free
+    # the activation pattern deviates from the oracle's only at pre-activations within rounding distance of zero
+    assert max(free["flip_worst_pre_rel"]) <= 1e-5, free
+    assert sum(free["flips"]) <= 1e-5 * sum(free["elements"]), free
+    # arithmetic parity of the backward pass: same pattern => every gradient within 1e-5 in both norms
+    assert max(pat["grad_max"]) <= 1e-5 and max(pat["grad_fro"]) <= 1e-5, pat
+    assert max(pat["hidden_bias_abs_over_scale"]) <= 1e-5, pat
+    # free-running gradients: Frobenius bound (each flip moves single entries of dW by O(1/N) of its scale)
+    assert max(free["grad_fro"]) <= 1e-4, free
