@@ -182,6 +182,60 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* _
   }
 }
 
+// Same pass on a BLOCK of the activation matrix: local rows r (global node id rowmap[r], or r + row_offset) and the
+// local columns [4*cv_off, 4*cv_off + 4*nvec_l) of a matrix that is nvec_g float4 wide globally.  The keep decision of
+// an element is the one affine_relu_dropout_kernel takes for the same (node, feature) of the full matrix, so any
+// row/column sharding and any node relabelling of the node-parallel engine reproduces the single-GPU mask bit for bit.
+template <bool P16>
+__global__ void __launch_bounds__(256) affine_relu_dropout_mapped_kernel(
+    const float* __restrict__ Y, float* __restrict__ out, int64_t n_rows, int nvec_l, const float* __restrict__ scale,
+    const float* __restrict__ shift, int relu, float p, uint32_t thr16, uint64_t seed, uint64_t offset,
+    const int32_t* __restrict__ step_dev, uint64_t step_mul, const int32_t* __restrict__ rowmap, uint64_t row_offset,
+    uint64_t nvec_g, uint64_t cv_off, int paired) {
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (step_dev) offset += (uint64_t)(*step_dev) * step_mul;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (P16 && paired) {                       // nvec_l, nvec_g, cv_off all even: one Philox block serves two float4s
+    const int half_l = nvec_l >> 1;
+    for (int64_t u = tid; u < n_rows * half_l; u += stride) {
+      const int64_t r = u / half_l;
+      const int cv = (int)(u - r * half_l) * 2;
+      const uint64_t gid = rowmap ? (uint64_t)rowmap[r] : (uint64_t)r + row_offset;
+      const uint64_t g = gid * nvec_g + cv_off + (uint64_t)cv;
+      const uint4 rnd = philox4x32(seed, offset, g >> 1);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int64_t i = r * nvec_l + cv + half;
+        float4 y = affine_relu4(ld4s(Y + 4 * i), scale, shift, cv + half, relu);
+        const uchar4 m = keep16(half ? rnd.z : rnd.x, half ? rnd.w : rnd.y, thr16);
+        y.x = m.x ? y.x * inv_keep : 0.f; y.y = m.y ? y.y * inv_keep : 0.f;
+        y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
+        st4(out + 4 * i, y);
+      }
+    }
+    return;
+  }
+  for (int64_t i = tid; i < n_rows * nvec_l; i += stride) {
+    const int64_t r = i / nvec_l;
+    const int cv = (int)(i - r * nvec_l);
+    float4 y = affine_relu4(ld4s(Y + 4 * i), scale, shift, cv, relu);
+    if (p > 0.f) {
+      const uint64_t gid = rowmap ? (uint64_t)rowmap[r] : (uint64_t)r + row_offset;
+      const uint64_t g = gid * nvec_g + cv_off + (uint64_t)cv;
+      uchar4 m;
+      if (P16) {
+        const uint4 rnd = philox4x32(seed, offset, g >> 1);
+        m = keep16((g & 1) ? rnd.z : rnd.x, (g & 1) ? rnd.w : rnd.y, thr16);
+      } else {
+        m = keep24(philox4x32(seed, offset, g), p);
+      }
+      y.x = m.x ? y.x * inv_keep : 0.f; y.y = m.y ? y.y * inv_keep : 0.f;
+      y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
+    }
+    st4(out + 4 * i, y);
+  }
+}
+
 // The keep-mask the kernel above uses, materialised (tests inject it into the CPU oracle).
 __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n_vec, float p, int p16,
                                                            uint32_t thr16, uint64_t seed, uint64_t offset) {
@@ -375,6 +429,34 @@ extern "C" int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64
     affine_relu_dropout_kernel<false><<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
         Y, out, n_vec, (int)(K / 4), scale, shift, relu, p, 0u, seed, offset, step_dev, step_mul,
         row_offset * (uint64_t)(K / 4));
+  return check_launch();
+}
+
+// Block form of the pass above (node-parallel engine): rows are nodes rowmap[r] (or r + row_offset), columns are
+// [col_offset, col_offset + K) of a K_global-wide activation matrix; masks equal the single-GPU ones elementwise.
+extern "C" int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                                      const float* scale, const float* shift, int relu, float p,
+                                                      uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                                                      uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
+                                                      int64_t K_global, int64_t col_offset, void* stream) {
+  if (!rows_ok(n_rows, K) || !Y || !out || p < 0.f || p >= 1.f || ((scale == nullptr) != (shift == nullptr)) ||
+      !aligned_to(Y, 16) || !aligned_to(out, 16) || K_global < K || K_global % 4 || col_offset < 0 || col_offset % 4 ||
+      col_offset + K > K_global)
+    return B200GNN_ERR_BAD_ARG;
+  if (n_rows == 0) return B200GNN_OK;
+  const int nvec_l = (int)(K / 4);
+  const uint64_t nvec_g = (uint64_t)(K_global / 4), cv_off = (uint64_t)(col_offset / 4);
+  const int paired = (nvec_l % 2 == 0 && nvec_g % 2 == 0 && cv_off % 2 == 0) ? 1 : 0;
+  const int64_t n_vec = n_rows * nvec_l;
+  uint32_t thr16 = 0;
+  if (dropout_p16(p, thr16))
+    affine_relu_dropout_mapped_kernel<true><<<grid_for(paired ? n_vec / 2 : n_vec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+        Y, out, n_rows, nvec_l, scale, shift, relu, p, thr16, seed, offset, step_dev, step_mul, rowmap, row_offset, nvec_g,
+        cv_off, paired);
+  else
+    affine_relu_dropout_mapped_kernel<false><<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        Y, out, n_rows, nvec_l, scale, shift, relu, p, 0u, seed, offset, step_dev, step_mul, rowmap, row_offset, nvec_g,
+        cv_off, 0);
   return check_launch();
 }
 

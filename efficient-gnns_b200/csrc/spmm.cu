@@ -42,6 +42,7 @@ struct SpmmParams {
   int32_t n_rows, K, nvec;
   int32_t hub_threshold, seg_len, n_hub, n_seg, n_chunks;
   int32_t mean, stream_store, main_grid;
+  int32_t n_slabs, l2_hint;   // bulk kernel: column slabs (slab-major grid), evict_last policy on the gathers
 };
 
 struct LaneMap {
@@ -216,7 +217,8 @@ __device__ __forceinline__ void spmm_chunk_cta(const SpmmParams& p, const int ct
 // combine in warp order through shared memory; raw (un-normalised) partials go
 // to the workspace.
 template <typename V, int CH, bool HAS_VAL>
-__device__ __forceinline__ void spmm_hub_seg_cta(const SpmmParams& p, const int seg, float* s_buf) {
+__device__ __forceinline__ void spmm_hub_seg_cta(const SpmmParams& p, const int seg, float* s_buf, const int slab_lo = 0,
+                                                 const int slab_hi = 1 << 30) {
   constexpr int W = VecTraits<V>::W;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,7 +245,7 @@ __device__ __forceinline__ void spmm_hub_seg_cta(const SpmmParams& p, const int 
   const int wend = min(send, wbeg + per);
 
   float* ws = p.hub_ws + (size_t)seg * p.K;
-  for (int slab = 0; slab < nslab; ++slab) {
+  for (int slab = slab_lo; slab < min(nslab, slab_hi); ++slab) {
     const int slab_voff = slab * slab_vecs;
     V acc[CH];
 #pragma unroll
@@ -460,6 +462,233 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_pipe_kernel(const S
 }
 
 
+// ------------------------------------------------------------------ bulk-copy (TMA) chunk kernel, column-slab tiled
+// Blackwell data path for wide rows (K a multiple of 128 floats).  Same chunk / run / row-boundary ownership as the
+// cp.async kernel above, but every neighbour row (slab) is ONE cp.async.bulk (SASS UBLKCP) of 512*CH bytes issued by the
+// lane that holds its column index, completing on an mbarrier per group of G ring slots: no per-lane copy instructions,
+// no address arithmetic on 32 lanes, and the ring keeps BULK_RING bytes per warp in flight across row boundaries.
+// K is tiled into column slabs of 128*CH floats and the grid is slab-major (all chunks of slab 0, then slab 1, ...), so
+// the [N, slab] operand the resident CTAs gather from is 1/n_slabs of X and stays L2-resident (ARXIV-shape K=256: 87 MB
+// per slab against a 126 MB L2, instead of 173 MB that does not fit); (col,val) are re-read per slab (8 B per edge).
+constexpr int BULK_RING = 8192;                  // ring bytes per warp
+constexpr int BULK_MAX_GROUPS = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+                   "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+template <int CH, int G, bool HAS_VAL, bool STATS>
+__device__ __forceinline__ void spmm_chunk_cta_bulk(const SpmmParams& p, const int cta, const int slab, float* s_stat,
+                                                    float4* ring_all, uint64_t* bars_all) {
+  constexpr int SLOT_V = CH * 32;                 // float4 per ring slot (one neighbour row of the slab)
+  constexpr int SLOT_B = SLOT_V * 16;
+  constexpr int D = BULK_RING / SLOT_B;           // ring depth in neighbour rows
+  constexpr int NG = D / G;                       // barrier groups in flight
+  static_assert(NG >= 2 && NG <= BULK_MAX_GROUPS && (32 % G) == 0 && D <= 32, "ring geometry");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* ring = ring_all + (size_t)warp * (BULK_RING / 16);
+  uint64_t* bars = bars_all + warp * BULK_MAX_GROUPS;
+  if (lane < NG) mbar_init(bars + lane, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  uint64_t pol = 0;
+  if (p.l2_hint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+
+  const int slab_voff = slab * SLOT_V;
+  const float4* Xv = reinterpret_cast<const float4*>(p.X) + slab_voff;
+  float4* Yv = reinterpret_cast<float4*>(p.Y) + slab_voff;
+  const size_t ldxv = (size_t)(p.ldx / 4), ldyv = (size_t)(p.ldy / 4);
+
+  float4 ssum[CH], ssq[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) { vzero(ssum[j]); vzero(ssq[j]); }
+  float4 bias4[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    vzero(bias4[j]);
+    if (p.bias) bias4[j] = load_bias<float4>(p.bias, slab_voff + lane + 32 * j);
+  }
+
+  const int chunk = cta * SPMM_WARPS + warp;
+  const int row_lo = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk) : 0;
+  const int row_hi = chunk < p.n_chunks ? __ldg(p.chunk_rowptr + chunk + 1) : 0;
+
+  auto flush = [&](int row, int deg, float4 (&acc)[CH]) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      float4 y = acc[j];
+      if (p.mean) vdiv(y, (float)max(deg, 1));
+      vadd(y, bias4[j]);
+      float4* dst = Yv + (size_t)row * ldyv + lane + 32 * j;
+      if (p.stream_store) vstcs(dst, y); else *dst = y;
+      if (STATS) vstat(ssum[j], ssq[j], y);
+      vzero(acc[j]);
+    }
+  };
+
+  uint32_t phases = 0;                           // bit b = parity the next wait on barrier b expects
+  int r = row_lo;
+  while (r < row_hi) {
+    // ---- a run [r, run_end) of consecutive non-hub rows; hub rows belong to the split path
+    int e_lo = __ldg(p.rowptr + r);
+    {
+      const int e_next = __ldg(p.rowptr + r + 1);
+      if (e_next - e_lo > p.hub_threshold) { ++r; continue; }
+    }
+    int run_end = r + 1, e_hi = __ldg(p.rowptr + r + 1);
+    while (run_end < row_hi) {
+      const int nx = __ldg(p.rowptr + run_end + 1);
+      if (nx - e_hi > p.hub_threshold) break;
+      e_hi = nx; ++run_end;
+    }
+    const int n = e_hi - e_lo;
+
+    int rbase = r;                                // row ends of the run, 32 at a time in registers
+    int rp = (rbase + lane < run_end) ? __ldg(p.rowptr + rbase + lane + 1) : e_hi;
+    auto row_end_of = [&](int row) {
+      if (row - rbase >= 32) {                    // warp-uniform
+        rbase = row;
+        rp = (rbase + lane < run_end) ? __ldg(p.rowptr + rbase + lane + 1) : e_hi;
+      }
+      return __shfl_sync(FULL_MASK, rp, row - rbase);
+    };
+
+    float4 acc[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) vzero(acc[j]);
+    int row_beg = e_lo;
+    int rend = row_end_of(r);
+    while (r < run_end && rend == row_beg) {      // leading empty rows
+      flush(r, 0, acc);
+      ++r;
+      if (r < run_end) rend = row_end_of(r);
+    }
+    if (n == 0) continue;
+
+    // Issue side: a 32-edge register window of column indices (cI); the lane that holds edge j's column issues its copy.
+    int cI = 0;
+    float vA = 1.f;
+    auto issue_group = [&](int jg, int slot0, int b) {    // edges jg..jg+G-1 (relative to e_lo) -> slots slot0.., barrier b
+      if (jg >= n) return;                                 // warp-uniform
+      if ((jg & 31) == 0) { const int e = e_lo + jg + lane; cI = e < e_hi ? __ldg(p.col + e) : 0; }
+      const int cnt = min(G, n - jg);
+      if (lane == 0) mbar_expect_tx(bars + b, (uint32_t)(cnt * SLOT_B));
+      const int u = lane - (jg & 31);
+      if (u >= 0 && u < cnt) {
+        const float4* src = Xv + (size_t)cI * ldxv;
+        float4* dst = ring + (slot0 + u) * SLOT_V;
+        if (p.l2_hint) bulk_g2s_hint(dst, src, SLOT_B, bars + b, pol);
+        else bulk_g2s(dst, src, SLOT_B, bars + b);
+      }
+    };
+    auto boundary = [&]() {                          // the current row is complete: store it (+ empty rows that follow)
+      do {
+        flush(r, rend - row_beg, acc);
+        row_beg = rend;
+        ++r;
+        if (r < run_end) rend = row_end_of(r);
+      } while (r < run_end && rend == row_beg);
+    };
+    auto consume_group = [&](int j0, int slot0) {    // j0 < n
+      if (HAS_VAL && (j0 & 31) == 0) { const int e = e_lo + j0 + lane; vA = e < e_hi ? __ldg(p.val + e) : 0.f; }
+      const float4* sbase = ring + slot0 * SLOT_V + lane;
+      const int cnt = min(G, n - j0);
+      int done = 0;
+      while (done < cnt) {                           // pieces of the group that lie in one row (all warp-uniform)
+        const int room = rend - (e_lo + j0 + done);  // >= 1: edges left in the current row
+        const int take = min(cnt - done, room);
+        if (take == G) {                             // common case: the whole group inside one row
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, (j0 + u) & 31) : 1.f;
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, sbase[u * SLOT_V + 32 * jj]);
+          }
+        } else {
+#pragma unroll 1
+          for (int u = done; u < done + take; ++u) {
+            const float w = HAS_VAL ? __shfl_sync(FULL_MASK, vA, (j0 + u) & 31) : 1.f;
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) vfma(acc[jj], w, sbase[u * SLOT_V + 32 * jj]);
+          }
+        }
+        done += take;
+        if (take == room) boundary();
+      }
+    };
+#pragma unroll
+    for (int g = 0; g < NG; ++g) issue_group(g * G, g * G, g);
+    int b = 0;
+#pragma unroll 1
+    for (int j = 0, s0 = 0; j < n; j += G) {
+      mbar_wait(bars + b, (phases >> b) & 1u);     // this group's rows have landed (complete_tx of all its copies)
+      phases ^= 1u << b;
+      consume_group(j, s0);
+      __syncwarp();                                // every lane has read the slots before they are refilled
+      issue_group(j + D, s0, b);
+      s0 = (s0 + G) & (D - 1);
+      b = (b + 1 == NG) ? 0 : b + 1;
+    }
+  }
+
+  if (STATS) {
+    constexpr int SW = SLOT_V * 4;                 // slab width in floats
+    float* ss = s_stat;
+    float* sq = s_stat + SW;
+    for (int i = threadIdx.x; i < 2 * SW; i += SPMM_THREADS) s_stat[i] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < SPMM_WARPS; ++w) {          // fixed order => deterministic
+      if (warp == w) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) smem_accum(ss, sq, lane + 32 * j, ssum[j], ssq[j]);
+      }
+      __syncthreads();
+    }
+    float* out = p.stat_partial + (size_t)cta * 2 * p.K + slab * SW;
+    for (int i = threadIdx.x; i < SW; i += SPMM_THREADS) { out[i] = ss[i]; out[p.K + i] = sq[i]; }
+  }
+}
+
+constexpr int BULK_SMEM = SPMM_WARPS * BULK_RING + SPMM_WARPS * BULK_MAX_GROUPS * 8;
+
+template <int CH, int G, bool HAS_VAL, bool STATS>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_bulk_kernel(const SpmmParams p) {
+  __shared__ float s_mem[2 * SPMM_MAX_SLAB_FLOATS];
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  const int per_slab = p.main_grid + p.n_seg;
+  const int slab = (int)blockIdx.x / per_slab;
+  const int b = (int)blockIdx.x - slab * per_slab;
+  if (b < p.n_seg) spmm_hub_seg_cta<float4, CH, HAS_VAL>(p, b, s_mem, slab, slab + 1);
+  else spmm_chunk_cta_bulk<CH, G, HAS_VAL, STATS>(p, b - p.n_seg, slab, s_mem, reinterpret_cast<float4*>(s_dyn),
+                                                  reinterpret_cast<uint64_t*>(s_dyn + SPMM_WARPS * BULK_RING));
+}
+
+
 // ------------------------------------------------------------------ narrow rows (K <= 64 floats: e.g. the 40 logits)
 // A 160-byte row needs only 10 lanes.  Instead of folding several NEIGHBOURS of one row across the warp (which drains
 // at every row end and needs cross-group shuffles), each group of lanes takes its OWN ROW of the chunk: 3 rows
@@ -613,13 +842,15 @@ static int launch_spmm_pipe(const SpmmParams& p, cudaStream_t st) {
   int rc;
   const bool stats = p.stat_partial != nullptr;
   const int grid = p.main_grid + p.n_seg;
-  static bool attr_done = false;
-  if (!attr_done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_done_dev[64] = {};
+  if (dev >= 0 && dev < 64 && !attr_done_dev[dev]) {
     cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
     cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
     cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
     cudaFuncSetAttribute(spmm_rows_pipe_kernel<CH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
-    attr_done = true;
+    attr_done_dev[dev] = true;
   }
   if (p.val) {
     if (stats) spmm_rows_pipe_kernel<CH, true, true><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
@@ -627,6 +858,36 @@ static int launch_spmm_pipe(const SpmmParams& p, cudaStream_t st) {
   } else {
     if (stats) spmm_rows_pipe_kernel<CH, false, true><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
     else spmm_rows_pipe_kernel<CH, false, false><<<grid, SPMM_THREADS, PIPE_SMEM, st>>>(p);
+  }
+  if ((rc = check_launch())) return rc;
+  if (p.n_hub > 0) {
+    spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);
+    if ((rc = check_launch())) return rc;
+  }
+  return B200GNN_OK;
+}
+
+template <int CH, int G>
+static int launch_spmm_bulk(const SpmmParams& p, cudaStream_t st) {
+  int rc;
+  const bool stats = p.stat_partial != nullptr;
+  const int grid = (p.main_grid + p.n_seg) * p.n_slabs;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool attr_done[64] = {};                  // per device (cudaFuncSetAttribute is per device); idempotent if raced
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    cudaFuncSetAttribute(spmm_rows_bulk_kernel<CH, G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM);
+    cudaFuncSetAttribute(spmm_rows_bulk_kernel<CH, G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM);
+    cudaFuncSetAttribute(spmm_rows_bulk_kernel<CH, G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM);
+    cudaFuncSetAttribute(spmm_rows_bulk_kernel<CH, G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BULK_SMEM);
+    attr_done[dev] = true;
+  }
+  if (p.val) {
+    if (stats) spmm_rows_bulk_kernel<CH, G, true, true><<<grid, SPMM_THREADS, BULK_SMEM, st>>>(p);
+    else spmm_rows_bulk_kernel<CH, G, true, false><<<grid, SPMM_THREADS, BULK_SMEM, st>>>(p);
+  } else {
+    if (stats) spmm_rows_bulk_kernel<CH, G, false, true><<<grid, SPMM_THREADS, BULK_SMEM, st>>>(p);
+    else spmm_rows_bulk_kernel<CH, G, false, false><<<grid, SPMM_THREADS, BULK_SMEM, st>>>(p);
   }
   if ((rc = check_launch())) return rc;
   if (p.n_hub > 0) {
@@ -729,8 +990,17 @@ __global__ void __launch_bounds__(256) chunk_plan_kernel(const int32_t* __restri
 
 using namespace b200gnn;
 
-// 0 = automatic (pipelined kernel where eligible), 1 = always the register-staged kernel (tuning / A-B tests)
+// see the variant word in b200gnn_spmm_csr_f32
 static int g_spmm_variant = 0;
+
+// Slab width (floats) the bulk kernel uses when left to choose.  Measured on B200 (ARXIV-shape, profiles/r2_spmm_sweep):
+// the copy engine retires ~20 G row copies/s chip-wide whatever their size (tools/bulk_probe.cu), so narrower slabs
+// lose more to the per-copy cost than their L2 residency wins back (K=256: one 1 KB copy per neighbour 0.263 ms,
+// two 512 B slabs 0.37 ms): take the widest slab the ring supports.
+static int bulk_auto_slab(int64_t K, int64_t n_src) {
+  (void)n_src;
+  return (K % 256 == 0) ? 256 : 128;
+}
 extern "C" void b200gnn_spmm_set_variant(int v) { g_spmm_variant = v; }
 
 extern "C" int64_t b200gnn_csr_chunk_count(int64_t n_rows, int64_t nnz, int32_t chunk_nnz, int32_t row_cost) {
@@ -802,18 +1072,38 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   if (K % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned_to(X, 16) && aligned_to(Y, 16)) W = 4;
   else if (K % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && aligned_to(X, 8) && aligned_to(Y, 8)) W = 2;
   p.nvec = (int32_t)(K / W);
-  const int ch = p.nvec <= 32 ? 1 : (p.nvec <= 64 ? 2 : 4);
-  const bool single_slab = p.nvec <= 32 * ch;
+  p.n_slabs = 1; p.l2_hint = 0;
+
+  // Variant word (b200gnn_spmm_set_variant; tuning and A/B tests): low nibble = kernel family
+  //   0 automatic, 1 register-staged, 2 cp.async ring (round-1 kernel), 3 bulk-copy ring, one slab of min(K,256) floats
+  //   per pass, 4 bulk-copy ring with 128-float slabs, 5 bulk-copy ring with 256-float slabs;
+  //   +16 = evict_last L2 policy on the gathers, +32 = the other barrier-group size.
+  const int fam = g_spmm_variant & 15;
+  const bool alt_g = (g_spmm_variant & 32) != 0;
+  int bulk_sw = 0;                                  // slab width in floats (0 = not the bulk kernel)
+  if (W == 4 && K % 128 == 0 && K <= 4096) {
+    if (fam == 3) bulk_sw = (K % 256 == 0) ? 256 : 128;
+    else if (fam == 4) bulk_sw = 128;
+    else if (fam == 5) bulk_sw = (K % 256 == 0) ? 256 : 128;
+    else if (fam == 0) bulk_sw = bulk_auto_slab(K, n_src);
+  }
+  int rc;
   float* fused_stats = stat_partial;
+  bool single_slab = true;
+  if (bulk_sw) {
+    p.n_slabs = (int32_t)(K / bulk_sw);
+    p.l2_hint = (g_spmm_variant & 16) ? 1 : 0;
+    if (bulk_sw == 128) rc = alt_g ? launch_spmm_bulk<1, 2>(p, st) : launch_spmm_bulk<1, 4>(p, st);
+    else rc = alt_g ? launch_spmm_bulk<2, 2>(p, st) : launch_spmm_bulk<2, 4>(p, st);
+    return rc;                                      // statistics are fused per slab
+  }
+
+  const int ch = p.nvec <= 32 ? 1 : (p.nvec <= 64 ? 2 : 4);
+  single_slab = p.nvec <= 32 * ch;
   if (!single_slab) p.stat_partial = nullptr;  // stats by a separate pass below
 
-  int rc;
-  // measured on B200 (ARXIV-shape): the pipelined kernel wins at K=256 (0.29 vs 0.42 ms) and loses slightly at
-  // K=128 (0.26 vs 0.23 ms: per-edge bookkeeping is amortised over half the bytes), so it is used from K=256 up;
-  // variant 2 forces it for K=128 too.
-  const bool pipe_ok = (W == 4) && g_spmm_variant != 1 &&
-                       (p.nvec == 32 || p.nvec == 64 || p.nvec == 128);
-  const bool narrow_ok = (W == 4) && p.nvec <= 16 && !p.stat_partial && g_spmm_variant != 1;
+  const bool pipe_ok = (W == 4) && fam == 2 && (p.nvec == 32 || p.nvec == 64 || p.nvec == 128);
+  const bool narrow_ok = (W == 4) && p.nvec <= 16 && !p.stat_partial && fam != 1;
   if (narrow_ok) {
     rc = B200GNN_OK;
     const int grid = p.main_grid + p.n_seg;

@@ -1,4 +1,7 @@
-"""bench.py's N>1 arm: the same GCN + logit-KD training step, node-parallel over N GPUs (torchrun, one rank per GPU)."""
+"""bench.py's N>1 arm: the same GCN + logit-KD training step over N GPUs (torchrun, one rank per GPU).
+
+Default engine: hybrid.HybridGCNTrainer with peer-memory exchanges (B200GNN_DIST_MODE=hybrid-peer); other modes for A/B
+runs: hybrid-nccl (same layout, torch.distributed all-to-all) and allgather (round-1 node-parallel engine, dist.py)."""
 from __future__ import annotations
 
 import json
@@ -12,6 +15,7 @@ def run(args):
     import bench as B
     from . import lib, sparse, synthetic
     from .dist import ShardedGCNTrainer
+    from .hybrid import HybridGCNTrainer
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -24,10 +28,23 @@ def run(args):
     ei = ds.edge_index.to(dev)
     perm = (ei[1] * n + ei[0]).argsort()
     adj = sparse.SparseTensor(row=ei[1][perm], col=ei[0][perm], sparse_sizes=(n, n), is_sorted=True).to_symmetric()
-    tr = ShardedGCNTrainer(adj, B.DIMS, dropout=0.5, lr=0.01, seed=0)
-    nnz_global = torch.tensor([tr.nnz], device=dev, dtype=torch.long)
-    dist.all_reduce(nnz_global)
-    nnz = int(nnz_global.item())
+    mode = os.environ.get("B200GNN_DIST_MODE", "hybrid-peer")
+    if mode.startswith("hybrid"):
+        try:
+            tr = HybridGCNTrainer(adj, B.DIMS, dropout=0.5, lr=0.01, seed=0, exchange="peer" if mode == "hybrid-peer" else "nccl")
+        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container): same layout over NCCL
+            if mode != "hybrid-peer":
+                raise
+            if rank == 0:
+                print(f"[dist_bench] peer exchange unavailable ({type(e).__name__}: {e}); falling back to hybrid-nccl", flush=True)
+            mode = "hybrid-nccl"
+            tr = HybridGCNTrainer(adj, B.DIMS, dropout=0.5, lr=0.01, seed=0, exchange="nccl")
+        nnz = tr.Gfull.nnz
+    else:
+        tr = ShardedGCNTrainer(adj, B.DIMS, dropout=0.5, lr=0.01, seed=0)
+        nnz_global = torch.tensor([tr.nnz], device=dev, dtype=torch.long)
+        dist.all_reduce(nnz_global)
+        nnz = int(nnz_global.item())
     x_pad, y_loc, tr_loc, t_loc = tr.shard_inputs(ds.x, ds.y.squeeze(1), ds.split_idx["train"], ds.teacher_logits)
 
     graph = None
@@ -129,7 +146,11 @@ def run(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": B.workload_config(ds, nnz),
                 "engine": {
-                    "parallelism": f"node-parallel x{world}: degree-balanced row blocks, one NCCL all-gather per aggregation",
+                    "parallelism": (f"hybrid layout x{world}: node-parallel dense ops, feature-parallel wide aggregations over the "
+                                    f"replicated graph, R<->C exchanges by {'peer-memory stores + flag barrier' if mode == 'hybrid-peer' else 'NCCL all-to-all'}; "
+                                    "narrow (40-wide) aggregations row-sharded with an all-gather") if mode.startswith("hybrid")
+                    else f"node-parallel x{world}: degree-balanced row blocks, one NCCL all-gather per aggregation",
+                    "dist_mode": mode,
                     "cuda_graph": bool(graph), "exchange_bytes_received_per_rank_per_step": ex,
                     "nvlink_floor_ms": ex / 770e9 * 1e3,
                     "aggregations_executed": tr.aggregations_per_step()},

@@ -49,6 +49,8 @@ SIGNATURES = {
                                        _f32p, _f32p, _f32p, _f32p, _ptr]),
     "b200gnn_affine_relu_dropout_f32": (_int, [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _int, _f32, _u64, _u64,
                                                _i32p, _u64, _u64, _ptr]),
+    "b200gnn_affine_relu_dropout_mapped_f32": (_int, [_f32p, _f32p, _i64, _i64, _f32p, _f32p, _int, _f32, _u64, _u64,
+                                                      _i32p, _u64, _i32p, _u64, _i64, _i64, _ptr]),
     "b200gnn_dropout_mask_u8": (_int, [_ptr, _i64, _i64, _f32, _u64, _u64, _ptr]),
     "b200gnn_bn_act_bwd_f32": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _f32, _f32p, _f32p,
                                       _f32p, _f32p, _f32p, _i64, _f32p, _ptr]),
@@ -85,7 +87,21 @@ SIGNATURES = {
     "b200gnn_gat_bwd_rows_f32": (_int, [_i32p, _i32p, _f32p, _f32p, _i64, _f32p, _i64, _f32p, _f32p, _i64, _i64, _i64, _f32,
                                         _f32p, _f32p, _i32p, _i64, _i32, _i32, _i32p, _i32p, _i64, _i64, _f32p, _ptr]),
     "b200gnn_segment_sum_heads_f32": (_int, [_i32p, _i32p, _f32p, _i64, _i64, _f32p, _ptr]),
+    "b200gnn_typed_gather_f32": (_int, [_ptr, _ptr, _i32, _ptr, _ptr, _i64, _i64, _f32p, _i64, _i32p, _ptr]),
+    "b200gnn_typed_scatter_f32": (_int, [_f32p, _i64, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _i32, _ptr]),
+    "b200gnn_arena_alloc": (_int, [_i64, C.POINTER(C.c_void_p)]),
+    "b200gnn_arena_free": (_int, [_ptr]),
+    "b200gnn_ipc_get_handle": (_int, [_ptr, _ptr]),
+    "b200gnn_ipc_open_handle": (_int, [_ptr, C.POINTER(C.c_void_p)]),
+    "b200gnn_ipc_close_handle": (_int, [_ptr]),
+    "b200gnn_peer_copy2d_f32": (_int, [_ptr, _i32, _i64, _ptr]),
+    "b200gnn_peer_barrier": (_int, [_ptr, _i32, _i32, _ptr, _ptr, _ptr]),
 }
+
+
+class Copy2D(C.Structure):
+    """struct b200gnn_copy2d (include/b200gnn.h)."""
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("ld_dst", C.c_int64), ("ld_src", C.c_int64), ("rows", C.c_int64)]
 
 _lib = None
 

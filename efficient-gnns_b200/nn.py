@@ -298,6 +298,72 @@ class MessagePassing(torch.nn.Module):
         return inputs
 
 
+# ----------------------------------------------------------------------------- hetero input assembly (a14)
+class _GroupInput(torch.autograd.Function):
+    """h[i] = table[node_type[i]][local_node_idx[i]]; backward = deterministic typed scatter into the tables that need a
+    gradient (b200gnn_typed_gather_f32 / b200gnn_typed_scatter_f32)."""
+
+    @staticmethod
+    def forward(ctx, node_type, local_node_idx, in_channels, keys, *tables):
+        import ctypes as C
+        dev = node_type.device
+        if not node_type.is_cuda:
+            raise lib.B200GnnError("group_input: CUDA tensors only (no CPU fallback)")
+        n = node_type.numel()
+        n_tables = (max(keys) + 1) if keys else 1
+        if n_tables > 16:
+            raise lib.B200GnnError("group_input: at most 16 node types")
+        ptrs = (C.c_void_p * n_tables)()
+        rows = (C.c_int64 * n_tables)()
+        for k, t in zip(keys, tables):
+            if t.dim() != 2 or t.shape[1] != in_channels or t.dtype != torch.float32 or not t.is_contiguous():
+                raise lib.B200GnnError(f"group_input: table of type {k} must be contiguous fp32 [rows, {in_channels}]")
+            ptrs[k], rows[k] = t.data_ptr(), t.shape[0]
+        out = torch.empty(n, in_channels, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        nt, li = node_type.contiguous(), local_node_idx.contiguous()
+        lib.check(lib.load().b200gnn_typed_gather_f32(ptrs, rows, n_tables, nt.data_ptr(), li.data_ptr(), n, in_channels,
+                                                      out.data_ptr(), in_channels, err.data_ptr(), lib.stream_ptr()),
+                  "typed_gather_f32")
+        ctx.keys, ctx.shapes, ctx.n_tables = keys, [tuple(t.shape) for t in tables], n_tables
+        ctx.save_for_backward(nt, li)
+        ctx.err = err
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        import ctypes as C
+        nt, li = ctx.saved_tensors
+        n, F_ = d_out.shape
+        needs = ctx.needs_input_grad[4:]
+        grads = [torch.zeros(sh, device=d_out.device) if need else None for sh, need in zip(ctx.shapes, needs)]
+        if any(needs) and n:
+            big = int(max(sh[0] for sh in ctx.shapes)) + 1
+            order = torch.argsort(nt * big + li, stable=True)
+            ptrs = (C.c_void_p * ctx.n_tables)()
+            rows = (C.c_int64 * ctx.n_tables)()
+            for k, g, sh in zip(ctx.keys, grads, ctx.shapes):
+                rows[k] = sh[0]
+                if g is not None:
+                    ptrs[k] = g.data_ptr()
+            d = d_out.contiguous()
+            lib.check(lib.load().b200gnn_typed_scatter_f32(d.data_ptr(), d.stride(0), nt.data_ptr(), li.data_ptr(), order.data_ptr(),
+                                                           n, F_, ptrs, rows, ctx.n_tables, lib.stream_ptr()), "typed_scatter_f32")
+        return (None, None, None, None, *grads)
+
+
+def group_input(x_dict, emb_dict, node_type: torch.Tensor, local_node_idx: torch.Tensor, in_channels: int) -> torch.Tensor:
+    """RGCN.group_input (mag_pyg/gnn.py:111-124): the [n, in_channels] input of the sampled / full heterogeneous graph,
+    row i taken from the feature table (x_dict, int keys) or the embedding table (emb_dict, str keys as in the reference's
+    ParameterDict) of node_type[i] at local_node_idx[i].  Types without a table give zero rows, as in the reference."""
+    keys, tables = [], []
+    for k, x in x_dict.items():
+        keys.append(int(k)); tables.append(x)
+    for k, e in emb_dict.items():
+        keys.append(int(k)); tables.append(e)
+    return _GroupInput.apply(node_type, local_node_idx, int(in_channels), tuple(keys), *tables)
+
+
 # ----------------------------------------------------------------------------------------- utils
 def subgraph(subset, edge_index, edge_attr=None, relabel_nodes=False, num_nodes=None):
     """torch_geometric.utils.subgraph: induced subgraph, edge order preserved, ids = positions in subset."""

@@ -143,6 +143,22 @@ def affine_relu_dropout(y: torch.Tensor, scale=None, shift=None, relu: bool = Tr
     return out
 
 
+def affine_relu_dropout_mapped(y: torch.Tensor, scale=None, shift=None, relu: bool = True, p: float = 0.0, seed: int = 0,
+                               offset: int = 0, out: Optional[torch.Tensor] = None, step_dev: Optional[torch.Tensor] = None,
+                               step_mul: int = 0, rowmap: Optional[torch.Tensor] = None, row_offset: int = 0,
+                               k_global: Optional[int] = None, col_offset: int = 0) -> torch.Tensor:
+    """affine_relu_dropout on a row/column BLOCK of an [N, k_global] activation matrix: local row r is node
+    rowmap[r] (int32) or r + row_offset, local columns start at col_offset.  Masks match the full-matrix call."""
+    n, K = y.shape
+    if out is None:
+        out = torch.empty_like(y)
+    lib.check(lib.load().b200gnn_affine_relu_dropout_mapped_f32(
+        _f32(y, "y"), _f32(out, "out"), n, K, _f32(scale, "scale"), _f32(shift, "shift"), int(relu), p, seed, offset,
+        lib.dptr(step_dev, torch.int32, "step_dev"), step_mul, lib.dptr(rowmap, torch.int32, "rowmap"), row_offset,
+        K if k_global is None else k_global, col_offset, lib.stream_ptr()), "affine_relu_dropout_mapped_f32")
+    return out
+
+
 def dropout_mask(n_rows: int, K: int, p: float, seed: int, offset: int, device="cuda") -> torch.Tensor:
     """The keep-mask (uint8 [n,K]) that affine_relu_dropout uses for (seed, offset)."""
     mask = torch.empty(n_rows, K, dtype=torch.uint8, device=device)

@@ -158,6 +158,14 @@ int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64_t n_rows,
                                     uint64_t seed, uint64_t offset,
                                     const int32_t* step_dev, uint64_t step_mul,
                                     uint64_t row_offset, void* stream);
+/* Block form (node-parallel engine, SURVEY.md §8e "identical dropout masks by global node id"): local row r is node
+ * rowmap[r] (or r + row_offset when rowmap is NULL), local columns are [col_offset, col_offset + K) of a
+ * K_global-wide matrix; every keep decision equals the one the full-matrix call takes for that (node, feature). */
+int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                           const float* scale, const float* shift, int relu, float p,
+                                           uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                                           uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
+                                           int64_t K_global, int64_t col_offset, void* stream);
 int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p,
                             uint64_t seed, uint64_t offset, void* stream);
 /* Backward of out = dropout_p(relu(BN_train(Y))): given dOut, out (for the
@@ -351,6 +359,55 @@ int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const fl
 int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx,
                                   const float* vals, int64_t n_rows, int64_t H,
                                   float* out, void* stream);
+
+/* ------------------------------------------------------------------
+ * Peer-memory exchange of the node-parallel engine (no reference counterpart: the reference is
+ * single-GPU, arxiv_pyg/scripts/run_gcn.sh:24-28).  One process per GPU; each rank allocates an exchange arena,
+ * publishes its CUDA IPC handle (64 opaque bytes, exchanged by the host side, e.g. torch.distributed) and maps the
+ * peers' arenas.  Exchange steps are kernels that store directly into the consumers' arenas over NVLink, then a
+ * flag barrier:
+ *   b200gnn_peer_copy2d_f32 : n <= 16 strided block copies in one launch, dst_j[r, 0:width] = src_j[r, 0:width]
+ *                             (width % 4 == 0; 16-byte aligned bases and pitches); dst_j may be peer memory
+ *   b200gnn_peer_barrier    : peer_flags[q] = rank q's flag array (16 uint64 slots, zero-initialised, inside its
+ *                             arena) as mapped in THIS process (host array of `world` device pointers); stores
+ *                             epoch+1 into slot [rank] of every rank's array with release semantics at system
+ *                             scope, waits until its own slots all reached it, then bumps *epoch (device counter,
+ *                             so the call is CUDA-graph replayable).  A peer that never arrives sets *error = 1
+ *                             after ~2^27 polls instead of hanging the device.
+ * ------------------------------------------------------------------ */
+typedef struct b200gnn_copy2d {
+  float* dst;
+  const float* src;
+  int64_t ld_dst; /* floats */
+  int64_t ld_src; /* floats */
+  int64_t rows;
+} b200gnn_copy2d;
+int b200gnn_arena_alloc(int64_t bytes, void** out);
+int b200gnn_arena_free(void* ptr);
+int b200gnn_ipc_get_handle(const void* dev_ptr, void* handle64);
+int b200gnn_ipc_open_handle(const void* handle64, void** out);
+int b200gnn_ipc_close_handle(void* ptr);
+int b200gnn_peer_copy2d_f32(const b200gnn_copy2d* copies, int32_t n, int64_t width, void* stream);
+int b200gnn_peer_barrier(uint64_t* const* peer_flags, int32_t rank, int32_t world,
+                         uint64_t* epoch, int32_t* error, void* stream);
+
+/* ------------------------------------------------------------------
+ * Heterogeneous input assembly — RGCN.group_input, mag_pyg/gnn.py:111-124 (called from RGCN.forward :126-129):
+ *   out[i, :] = tables[node_type[i]][local_idx[i], :]     (tables[t] NULL or type out of range => zero row)
+ * node_type / local_idx are the int64 tensors of group_hetero_graph; tables / table_rows are HOST arrays of
+ * n_tables <= 16 device pointers / row counts.  An index outside its table sets *error_flag (device int32) to 1.
+ * typed_scatter is the backward: d_tables[t][j, :] = sum over nodes i with (node_type, local_idx) == (t, j) of
+ * d_out[i, :], written (not accumulated: untouched rows keep what the caller put there, normally zeros) for the
+ * tables whose pointer is non-NULL.  `order` = the node ids sorted by (node_type, local_idx) (stable): runs of equal
+ * keys are added in that order by one warp => deterministic, no atomics.
+ * ------------------------------------------------------------------ */
+int b200gnn_typed_gather_f32(const float* const* tables, const int64_t* table_rows, int32_t n_tables,
+                             const int64_t* node_type, const int64_t* local_idx, int64_t n, int64_t F,
+                             float* out, int64_t ldo, int32_t* error_flag, void* stream);
+int b200gnn_typed_scatter_f32(const float* d_out, int64_t ldd, const int64_t* node_type,
+                              const int64_t* local_idx, const int64_t* order, int64_t n, int64_t F,
+                              float* const* d_tables, const int64_t* table_rows, int32_t n_tables,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,10 +44,7 @@ class RelNet(torch.nn.Module):
         self.convs = torch.nn.ModuleList([RelConv(cin, hid, len(num_nodes), n_rels), RelConv(hid, cout, len(num_nodes), n_rels)])
 
     def forward(self, x_dict, edge_index, edge_type, node_type, local_idx):
-        h = torch.zeros(node_type.numel(), self.cin, device=node_type.device)
-        for key, x in list(x_dict.items()) + [(int(k), e) for k, e in self.emb_dict.items()]:
-            idx = (node_type == key).nonzero().view(-1)
-            h = h.index_add(0, idx, x[local_idx[idx]])
+        h = bnn.group_input(x_dict, self.emb_dict, node_type, local_idx, self.cin)     # mag_pyg/gnn.py:111-124
         self.out_feat = F.relu(self.convs[0](h, edge_index, edge_type, node_type))
         return self.convs[1](self.out_feat, edge_index, edge_type, node_type)
 
@@ -89,3 +86,33 @@ def test_rgcn_inference_matches_reference_class_fixture(golden_rgcn):
         out = net.inference({0: G["x_paper"].cuda()}, {k: v.cuda() for k, v in G["edge_index_dict"].items()}, G["key2int"])
     for t in range(3):
         assert rel_err(out[t], G["out_inference"][t]) < 1e-5
+
+
+def test_group_input_typed_gather_and_deterministic_scatter():
+    """RGCN.group_input (mag_pyg/gnn.py:111-124) against its torch restatement: duplicated (type, idx) pairs, a type with no
+    table (zero rows), bit-exact forward, gradient = index_put(accumulate) in fp64, bitwise repeatable."""
+    g = torch.Generator().manual_seed(0)
+    n, F_ = 5000, 128
+    sizes = {0: 700, 1: 300, 2: 40}
+    node_type = torch.randint(0, 4, (n,), generator=g)                    # type 3 has no table
+    local = torch.stack([torch.randint(0, sizes.get(int(t), 1), (1,), generator=g)[0] for t in node_type])
+    x_dict = {0: torch.randn(sizes[0], F_, generator=g).cuda()}
+    emb = torch.nn.ParameterDict({str(k): torch.nn.Parameter(torch.randn(sizes[k], F_, generator=g)) for k in (1, 2)}).cuda()
+    w = torch.randn(n, F_, generator=g).cuda()
+    nt, li = node_type.cuda(), local.cuda()
+    h = bnn.group_input(x_dict, emb, nt, li, F_)
+    ref = torch.zeros(n, F_, device="cuda")
+    for key, tab in [(0, x_dict[0]), (1, emb["1"]), (2, emb["2"])]:
+        m = nt == key
+        ref[m] = tab.detach()[li[m]]
+    assert torch.equal(h, ref)
+    (h * w).sum().backward()
+    for k in (1, 2):
+        m = nt == k
+        want = torch.zeros(sizes[k], F_, dtype=torch.float64, device="cuda").index_put_((li[m],), w[m].double(), accumulate=True)
+        assert rel_err(emb[str(k)].grad, want) < 1e-6
+    g1 = [emb[str(k)].grad.clone() for k in (1, 2)]
+    for k in (1, 2):
+        emb[str(k)].grad = None
+    (bnn.group_input(x_dict, emb, nt, li, F_) * w).sum().backward()
+    assert all(torch.equal(a, emb[str(k)].grad) for a, k in zip(g1, (1, 2)))

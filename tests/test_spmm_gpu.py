@@ -167,3 +167,67 @@ def test_large_arxiv_shape_properties():
     lhs = (ax.double() * y.double()).sum()
     rhs = (x.double() * xg.grad.double()).sum()
     assert abs(lhs - rhs) / abs(lhs) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- round 2: bulk-copy kernel
+# variant word: 2 = cp.async ring, 3 = bulk (slab min(K,256)), 4 = bulk 128-float slabs, 5 = bulk 256-float slabs,
+# +16 evict_last gathers, +32 other barrier-group size (efficient-gnns_b200/csrc/spmm.cu)
+BULK_VARIANTS = [0, 1, 2, 3, 4, 5, 3 + 16, 4 + 16, 3 + 32, 4 + 32, 5 + 16 + 32]
+
+
+@pytest.fixture
+def spmm_variant():
+    yield ops.set_spmm_variant
+    ops.set_spmm_variant(0)
+
+
+@pytest.mark.parametrize("K", [128, 256, 384, 512])
+@pytest.mark.parametrize("variant", BULK_VARIANTS)
+def test_spmm_bulk_variants_hubs_stats_bias(K, variant, spmm_variant):
+    """Every SpMM kernel family on a graph with a 12k hub, a 700-edge row, empty rows and runs that cross the 32-edge
+    windows; forward, fused bias + per-CTA column statistics, mean reduction; bitwise repeatable."""
+    n = 20_000
+    g = torch.Generator().manual_seed(11)
+    hub_nbrs = torch.randperm(n, generator=g)[:12_345]
+    mid_nbrs = torch.randperm(n, generator=g)[:700]
+    row = torch.cat([torch.full((12_345,), 7), torch.full((700,), 4000), torch.randint(100, n - 50, (150_000,), generator=g)])
+    col = torch.cat([hub_nbrs, mid_nbrs, torch.randint(0, n, (150_000,), generator=g)])
+    r, c, _ = og.coalesce(row.numpy(), col.numpy(), n)
+    r, c = torch.from_numpy(r), torch.from_numpy(c)
+    val = torch.rand(r.numel(), generator=g)
+    x, bias = torch.randn(n, K, generator=g), torch.randn(K, generator=g)
+    adj = make_adj(r, c, n, n, val)
+    G = adj.storage.engine_csr()
+    Gu = adj.set_value(None).storage.engine_csr_unweighted()
+    spmm_variant(variant)
+    ref = oo.spmm_scatter(r, c, val.double(), x.double(), n, "sum") + bias.double()
+    part = torch.full((ops.stat_slots(G), 2, K), float("nan"), device="cuda")
+    out = ops.spmm_csr(G, x.cuda(), "sum", bias=bias.cuda(), stat_partial=part)
+    assert rel_err(out, ref) < TOL and fro_err(out, ref) < TOL
+    s = part.double().sum(0).cpu()
+    assert rel_err(s[0], ref.sum(0)) < TOL and rel_err(s[1], (ref * ref).sum(0)) < TOL
+    part2 = torch.empty_like(part)
+    out2 = ops.spmm_csr(G, x.cuda(), "sum", bias=bias.cuda(), stat_partial=part2)
+    assert torch.equal(out, out2) and torch.equal(part, part2)
+    refm = oo.spmm_scatter(r, c, None, x.double(), n, "mean")
+    outm = ops.spmm_csr(Gu, x.cuda(), "mean")
+    assert rel_err(outm, refm) < TOL
+    assert torch.count_nonzero(outm[:7]) == 0            # empty rows -> exactly 0
+    assert rel_err(outm[7], refm[7]) < TOL and rel_err(outm[4000], refm[4000]) < TOL
+
+
+@pytest.mark.parametrize("variant", [3, 4, 4 + 16])
+def test_spmm_bulk_tiny_and_ragged(variant, spmm_variant):
+    """Degenerate shapes on the bulk kernel: a single edge, rows of degree exactly G / ring depth, a graph smaller than one
+    chunk, and a rectangular matrix whose sources are never referenced beyond n_src."""
+    spmm_variant(variant)
+    K = 256
+    g = torch.Generator().manual_seed(12)
+    for n_rows, n_cols, degs in [(1, 1, [1]), (5, 9, [0, 1, 0, 9, 2]), (40, 64, [4] * 8 + [8] * 8 + [16] * 8 + [0] * 8 + [33] * 8)]:
+        row = torch.cat([torch.full((d,), i) for i, d in enumerate(degs)]).long()
+        col = torch.cat([torch.randperm(n_cols, generator=g)[:d].sort().values for d in degs]).long()
+        x = torch.randn(n_cols, K, generator=g)
+        val = torch.rand(row.numel(), generator=g)
+        ref = oo.spmm_scatter(row, col, val.double(), x.double(), n_rows, "sum")
+        out = make_adj(row, col, n_rows, n_cols, val).matmul(x.cuda(), "sum")
+        assert rel_err(out, ref) < TOL
