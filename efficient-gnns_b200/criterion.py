@@ -304,6 +304,33 @@ class LspPlan:
         torch.cumsum(counts, 0, out=rowptr[1:])
         self.rowptr = rowptr.to(torch.int32).contiguous()
         self.edge_index = edge_index          # keeps the keyed storage alive: its address cannot be recycled while cached
+        self._bwd = {}
+
+    def backward_matrix(self, n_nodes: int):
+        """CSR structure of the backward matrix C (csrc/loss_edge.cu, b200gnn_lsp_bwd_values_f32) for `n_nodes` feature
+        rows: (CsrGraph with an in-place updatable value array, pos_dst, pos_src, diag_pos, selfc scratch)."""
+        hit = self._bwd.get(n_nodes)
+        if hit is not None:
+            return hit
+        from .sparse import csr_graph_from
+        dev, E = self.src.device, self.E
+        src, dst = self.src.long(), self.dst.long()
+        if E and int(max(src.max(), dst.max())) >= n_nodes:
+            raise lib.B200GnnError("LSP: edge_index refers to a node beyond the feature matrix")
+        ar = torch.arange(n_nodes, device=dev)
+        rows = torch.cat([dst, src, ar])
+        cols = torch.cat([src, dst, ar])
+        perm = torch.argsort(rows, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel(), device=dev)
+        rowptr = torch.zeros(n_nodes + 1, dtype=torch.long, device=dev)
+        torch.cumsum(torch.bincount(rows, minlength=n_nodes), 0, out=rowptr[1:])
+        val = torch.zeros(perm.numel(), device=dev)
+        G = csr_graph_from(rowptr, cols[perm], val, n_nodes, n_nodes)
+        pos = inv.to(torch.int32)
+        hit = (G, pos[:E].contiguous(), pos[E:2 * E].contiguous(), pos[2 * E:].contiguous(), torch.zeros_like(val))
+        self._bwd[n_nodes] = hit
+        return hit
 
     @classmethod
     def of(cls, edge_index: torch.Tensor) -> "LspPlan":
@@ -341,10 +368,15 @@ class _LSP(torch.autograd.Function):
     def backward(ctx, gout):
         feat, sim_s, g = ctx.saved_tensors
         plan = ctx.plan
-        d = torch.zeros_like(feat)
-        lib.check(_L().b200gnn_edge_sim_bwd_f32(_f32(feat, "feat"), feat.shape[1], plan.src.data_ptr(), plan.dst.data_ptr(),
-                                                plan.E, ctx.kernel, _f32(sim_s, "sim"), _f32(g, "g"), _f32(d, "d"),
-                                                lib.stream_ptr()), "edge_sim_bwd_f32")
+        n, F_ = feat.shape
+        G, pos_dst, pos_src, diag_pos, selfc = plan.backward_matrix(n)
+        lib.check(_L().b200gnn_lsp_bwd_values_f32(_f32(feat, "feat"), F_, plan.src.data_ptr(), plan.dst.data_ptr(), plan.E,
+                                                  ctx.kernel, _f32(sim_s, "sim"), _f32(g, "g"), pos_dst.data_ptr(),
+                                                  pos_src.data_ptr(), G.rowptr.data_ptr(), diag_pos.data_ptr(), n,
+                                                  _f32(G.val, "val"), _f32(selfc, "selfc"), lib.stream_ptr()),
+                  "lsp_bwd_values_f32")
+        from . import ops
+        d = ops.spmm_csr(G, feat, "sum")             # d feat = C · feat: fixed summation order, no atomics
         return d * gout, None, None, None, None
 
 
@@ -359,35 +391,70 @@ def lpw_criterion(logits, labels, feat, teacher_feat, edge_index, kernel='cosine
 
 
 # ----------------------------------------------------------------------------------------- G-CRD
+NCE_CHUNK_BYTES = 32 << 20      # logits chunk [R, S] (+ its transpose) sized to stay L2-resident between the three GEMMs
+
+
 class _NCE(torch.autograd.Function):
-    """InfoNCE between normalised student rows and teacher rows (criterion.py:139-146): one S x S x F contraction on the
-    tensor cores, row log-sum-exp + d/dlogits in one pass, two contractions back."""
+    """InfoNCE between normalised student rows and teacher rows (criterion.py:139-146) WITHOUT the S x S logits tensor
+    (1 GiB at the scripts' S = 16384, arxiv_pyg/scripts/run_gcn.sh:144).  The rows are streamed in chunks of R (R*S*4 <=
+    32 MB, so a chunk and its transpose live in the 126 MB L2): per chunk one [R,S] logits GEMM on the tensor cores, the
+    fused row pass (log-sum-exp, loss term, d/dlogits in place), and the two gradient contractions
+    d fs[chunk] = dZ_c · x_t and d f_t += dZ_c^T · x_s[chunk] (accumulating epilogue) — the gradients are complete when
+    the forward returns, so the backward only scales them."""
 
     @staticmethod
     def forward(ctx, fs, ft, nce_T: float):
         fs, ft = fs.contiguous(), ft.contiguous()
         L, st = _L(), lib.stream_ptr()
-        S = fs.shape[0]
+        S, F_ = fs.shape
         xs, ns = _normalize(fs, 1.0 / nce_T)          # logits / T folded into the student operand
         xt, nt = _normalize(ft)
-        Z = _gemm_nt(xs, xt)                           # [S,S]
-        loss, part = _new(1, like=fs), _new(S, like=fs)
-        lib.check(L.b200gnn_nce_rows_f32(_f32(Z, "Z"), S, _f32(loss, "loss"), _f32(part, "part"), st), "nce_rows_f32")
-        ctx.nce_T = nce_T
-        ctx.save_for_backward(xs, ns, xt, nt, Z)       # Z now holds d loss / d logits
+        # every matrix is zero-padded to multiples of 4 rows / columns (TMA row pitches): zero feature rows give zero
+        # logits, the row pass only visits the S real rows and columns, so the padding never reaches the result
+        xs_p, xt_p = _pad_k(_pad_k(xs, 1), 0), _pad_k(_pad_k(xt, 1), 0)
+        Sp, Fp = xs_p.shape
+        need_s, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        R = min(max(128, (NCE_CHUNK_BYTES // (4 * Sp)) // 128 * 128), Sp)
+        xt_hi, xt_lo = ops.split_tf32(xt_p)                              # B of Z_c = xs_c · xt^T         [Sp, Fp]
+        if need_s:
+            xtT_hi, xtT_lo = ops.split_tf32(xt_p, transpose=True)        # B of dZ_c · xt                   [Fp, Sp]
+            g_s = torch.empty(Sp, Fp, device=fs.device)
+        if need_t:
+            g_t = torch.zeros(Sp, Fp, device=fs.device)
+            Zt = _new(Sp * R, like=fs)
+        Z = _new(R, Sp, like=fs)
+        part = _new(S, like=fs)
+        for r0 in range(0, Sp, R):
+            r = min(R, Sp - r0)                                          # multiple of 4
+            Zc = Z[:r]
+            ops.gemm_tf32x3(xs_p[r0:r0 + r], xt_hi, xt_lo, out=Zc)
+            if r0 < S:
+                lib.check(L.b200gnn_nce_rows_chunk_f32(_f32(Zc, "Z"), Sp, min(r, S - r0), S, r0, _f32(part, "part"), st),
+                          "nce_rows_chunk_f32")
+            if need_s:
+                ops.gemm_tf32x3(Zc, xtT_hi, xtT_lo, out=g_s[r0:r0 + r])
+            if need_t:
+                Ztc = Zt[:Sp * r].view(Sp, r)
+                lib.check(L.b200gnn_transpose_f32(_f32(Zc, "Z"), r, Sp, _f32(Ztc, "Zt"), st), "transpose_f32")
+                hi, lo = ops.split_tf32(xs_p[r0:r0 + r], transpose=True)                  # [Fp, r]
+                ops.gemm_tf32x3(Ztc, hi, lo, out=g_t, accumulate=True)
+        loss = _new(1, like=fs)
+        lib.check(L.b200gnn_nce_finish_f32(_f32(part, "part"), S, _f32(loss, "loss"), st), "nce_finish_f32")
+        saved = []
+        if need_s:
+            saved.append(_normalize_bwd(xs, ns, g_s[:S, :F_], 1.0 / nce_T))
+        if need_t:
+            saved.append(_normalize_bwd(xt, nt, g_t[:S, :F_]))
+        ctx.flags = (need_s, need_t)
+        ctx.save_for_backward(*saved)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        xs, ns, xt, nt, dZ = ctx.saved_tensors
-        L, st = _L(), lib.stream_ptr()
-        d_fs = d_ft = None
-        if ctx.needs_input_grad[0]:
-            d_fs = _normalize_bwd(xs, ns, _gemm_nn(dZ, xt), 1.0 / ctx.nce_T) * g
-        if ctx.needs_input_grad[1]:
-            dZt = torch.empty_like(dZ)
-            lib.check(L.b200gnn_transpose_f32(_f32(dZ, "dZ"), dZ.shape[0], dZ.shape[1], _f32(dZt, "dZt"), st), "transpose_f32")
-            d_ft = _normalize_bwd(xt, nt, _gemm_nn(dZt, xs)) * g
+        need_s, need_t = ctx.flags
+        saved = list(ctx.saved_tensors)
+        d_fs = saved.pop(0) * g if need_s else None
+        d_ft = saved.pop(0) * g if need_t else None
         return d_fs, d_ft, None
 
 

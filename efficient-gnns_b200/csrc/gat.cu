@@ -66,6 +66,7 @@ __device__ __forceinline__ void reduce_heads(float (&v)[GAT_MAXH], int H, float 
 // ---------------------------------------------------------------- edge softmax: a[e,h]
 struct GatSoftmax {
   const int32_t* rowptr; const int32_t* col; const float* el; const float* er; float* a;
+  const uint8_t* keep;   // [nnz] or NULL: edges with keep == 0 are dropped (a = 0, excluded from the softmax) — edge_drop
   int64_t n_rows; int32_t H; float slope, eps;
 };
 
@@ -80,6 +81,7 @@ __device__ __forceinline__ void softmax_row(const GatSoftmax& p, int64_t i, int 
     s[h] = 0.f;
   }
   for (int k = b + tid; k < e; k += nt) {
+    if (p.keep && !p.keep[k]) continue;
     const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h)
@@ -87,6 +89,7 @@ __device__ __forceinline__ void softmax_row(const GatSoftmax& p, int64_t i, int 
   }
   reduce_heads<CTA, true>(m, p.H, s_red, lane, warp);
   for (int k = b + tid; k < e; k += nt) {
+    if (p.keep && !p.keep[k]) continue;
     const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h)
@@ -94,10 +97,11 @@ __device__ __forceinline__ void softmax_row(const GatSoftmax& p, int64_t i, int 
   }
   reduce_heads<CTA, false>(s, p.H, s_red, lane, warp);
   for (int k = b + tid; k < e; k += nt) {
+    const bool kept = !p.keep || p.keep[k];
     const float* x = p.el + (size_t)__ldg(p.col + k) * p.H;
 #pragma unroll
     for (int h = 0; h < GAT_MAXH; ++h)
-      if (h < p.H) p.a[(size_t)k * p.H + h] = expf(lrelu(__ldg(x + h) + r[h], p.slope) - m[h]) / (s[h] + p.eps);
+      if (h < p.H) p.a[(size_t)k * p.H + h] = kept ? expf(lrelu(__ldg(x + h) + r[h], p.slope) - m[h]) / (s[h] + p.eps) : 0.f;
   }
 }
 
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__(GAT_THREADS) gat_hub_finalize_kernel(const int
 struct GatBwd {
   const int32_t* rowptr; const int32_t* col; const float* a; const float* ft; const float* dout;
   const float* el; const float* er;
+  const float* scale;   // [nnz,H] or NULL: attention dropout, the aggregation used a*scale (scale = keep/(1-p)); d a = d(a*scale)*scale
   float* dpre;   // [nnz,H]  out: d loss / d (el[src]+er[dst])
   float* der;    // [n_rows,H] out (may be NULL when there is no er)
   const int32_t* chunk_rowptr; const int32_t* hub_rows; const int32_t* hub_segptr;
@@ -342,8 +347,9 @@ __device__ __forceinline__ void bwd_edges(const GatBwd& p, int beg, int end, int
               if (o < lph) d[j] += __shfl_xor_sync(FULL_MASK, d[j], o);
             if (lane + 32 * j < nvec) {
               const size_t o = (size_t)kk * p.H + head[j];
-              if ((lane & (lph - 1)) == 0) p.dpre[o] = d[j];
-              Sj[j] = fmaf(__ldg(p.a + o), d[j], Sj[j]);
+              const float da = p.scale ? d[j] * __ldg(p.scale + o) : d[j];
+              if ((lane & (lph - 1)) == 0) p.dpre[o] = da;
+              Sj[j] = fmaf(__ldg(p.a + o), da, Sj[j]);
             }
           }
         } else {
@@ -353,8 +359,8 @@ __device__ __forceinline__ void bwd_edges(const GatBwd& p, int beg, int end, int
               float part = 0.f;
 #pragma unroll
               for (int j = 0; j < NJ; ++j) part += (head[j] == h) ? d[j] : 0.f;
-              const float da = gsum(part);
               const size_t o = (size_t)kk * p.H + h;
+              const float da = p.scale ? gsum(part) * __ldg(p.scale + o) : gsum(part);
               if (lane == 0) p.dpre[o] = da;
               S[h] = fmaf(__ldg(p.a + o), da, S[h]);
             }
@@ -570,11 +576,11 @@ using namespace b200gnn;
 
 extern "C" int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t* col, const float* el, const float* er,
                                             int64_t n_rows, int64_t H, float negative_slope, float softmax_eps, float* a,
-                                            void* stream) {
+                                            const uint8_t* edge_keep, void* stream) {
   if (!rowptr || !el || !a || n_rows < 0 || H <= 0 || H > GAT_MAXH) return B200GNN_ERR_BAD_ARG;
   if (n_rows == 0) return B200GNN_OK;
   GatSoftmax p;
-  p.rowptr = rowptr; p.col = col; p.el = el; p.er = er; p.a = a; p.n_rows = n_rows; p.H = (int32_t)H;
+  p.rowptr = rowptr; p.col = col; p.el = el; p.er = er; p.a = a; p.keep = edge_keep; p.n_rows = n_rows; p.H = (int32_t)H;
   p.slope = negative_slope; p.eps = softmax_eps;
   gat_edge_softmax_kernel<<<rows_grid(n_rows), GAT_THREADS, 0, (cudaStream_t)stream>>>(p);
   return check_launch();
@@ -613,7 +619,7 @@ extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* co
                                         int64_t H, int64_t D, float negative_slope, float* dpre, float* der,
                                         const int32_t* chunk_rowptr, int64_t n_chunks, int32_t hub_threshold,
                                         int32_t seg_len, const int32_t* hub_rows, const int32_t* hub_segptr, int64_t n_hub,
-                                        int64_t n_seg, float* hub_workspace, void* stream) {
+                                        int64_t n_seg, float* hub_workspace, const float* attn_scale, void* stream) {
   const int64_t K = H * D;
   if (!rowptr || !a || !ft || !dout || !el || !dpre || n_rows < 0 || H <= 0 || D <= 0 || H > GAT_MAXH || ldf < K || ldd < K ||
       !chunk_rowptr || n_chunks < 0 || n_hub < 0 || n_seg < n_hub ||
@@ -622,6 +628,7 @@ extern "C" int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* co
   if (n_rows == 0 || n_chunks == 0) return B200GNN_OK;
   GatBwd p;
   p.rowptr = rowptr; p.col = col; p.a = a; p.ft = ft; p.dout = dout; p.el = el; p.er = er; p.dpre = dpre; p.der = der;
+  p.scale = attn_scale;
   p.chunk_rowptr = chunk_rowptr; p.hub_rows = hub_rows; p.hub_segptr = hub_segptr; p.ws = hub_workspace;
   p.ldf = ldf; p.ldd = ldd; p.n_rows = n_rows; p.n_chunks = (int32_t)n_chunks; p.n_hub = (int32_t)n_hub;
   p.n_seg = (int32_t)(n_hub > 0 ? n_seg : 0); p.seg_len = seg_len;

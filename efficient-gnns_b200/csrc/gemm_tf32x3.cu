@@ -73,6 +73,7 @@ struct Params {
   const float* bias;
   int64_t ldc;
   int32_t M, N, K;
+  int32_t accumulate;   // C += A·B^T (+bias) instead of C = ...
 };
 
 template <class C>
@@ -218,14 +219,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int grow = m0 + q * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(tile + rr * EPI_LD + cq);
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (grow < p.M) *reinterpret_cast<float4*>(p.C + (size_t)grow * p.ldc + col0 + cq) = v;
+            if (grow < p.M) {
+              float4* dst = reinterpret_cast<float4*>(p.C + (size_t)grow * p.ldc + col0 + cq);
+              if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              *dst = v;
+            }
           }
           __syncwarp();
         } else if (row < p.M && col0 < p.N) {
           float* dst = p.C + (size_t)row * p.ldc + col0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+            if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f) + (p.accumulate ? dst[j] : 0.f);
         }
       }
       tc_fence_before();
@@ -276,15 +281,15 @@ static int launch(const float* A, int64_t lda, const float* B_hi, const float* B
   if (!make_map(&tA, A, p.M, p.K, lda, BM) || !make_map(&tBh, B_hi, p.N, p.K, ldb, C::BN) ||
       !make_map(&tBl, B_lo, p.N, p.K, ldb, C::BN))
     return B200GNN_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
-    attr_set = true;
-  }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + C::BN - 1) / C::BN);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool attr_set[64] = {};                    // per device; idempotent if two threads race
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
+    attr_set[dev] = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + C::BN - 1) / C::BN);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = tiles < sms ? tiles : sms;
   gemm_tf32x3_kernel<C><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tA, tBh, tBl, p);
@@ -306,9 +311,8 @@ extern "C" int b200gnn_split_tf32_f32(const float* W, int64_t rows, int64_t cols
   return check_launch();
 }
 
-extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
-                                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                                       void* stream) {
+static int gemm_dispatch(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb, float* C, int64_t ldc,
+                         int64_t M, int64_t N, int64_t K, const float* bias, int accumulate, void* stream) {
   if (!A || !B_hi || !B_lo || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N ||
       M >= INT32_MAX || N >= INT32_MAX || K >= INT32_MAX)
     return B200GNN_ERR_BAD_ARG;
@@ -316,7 +320,19 @@ extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float*
   if (lda % 4 || ldb % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16))
     return B200GNN_ERR_UNSUPPORTED;
   gemm::Params p;
-  p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K;
+  p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = accumulate ? 1 : 0;
   if (N <= 48) return gemm::launch<gemm::Cfg<48, 4>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
   return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
+}
+
+extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                       float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                                       void* stream) {
+  return gemm_dispatch(A, lda, B_hi, B_lo, ldb, C, ldc, M, N, K, bias, 0, stream);
+}
+
+// C += A · B^T (same kernel; the epilogue adds the tile it is about to overwrite).  Used by the chunked G-CRD backward.
+extern "C" int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                           float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
+  return gemm_dispatch(A, lda, B_hi, B_lo, ldb, C, ldc, M, N, K, nullptr, 1, stream);
 }

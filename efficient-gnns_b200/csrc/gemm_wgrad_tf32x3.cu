@@ -226,12 +226,14 @@ extern "C" int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const 
     return B200GNN_ERR_UNSUPPORTED;
   CUtensorMap tX, tG;
   if (!wgrad::make_map_mn(&tX, X, Nn, Kin, ldx) || !wgrad::make_map_mn(&tG, G, Nn, Nout, ldg)) return B200GNN_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  int dev_a = 0;
+  cudaGetDevice(&dev_a);
+  static bool attr_set[64] = {};                    // per device
+  if (dev_a >= 0 && dev_a < 64 && !attr_set[dev_a]) {
     cudaError_t e = cudaFuncSetAttribute(wgrad::wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          wgrad::SMEM_BYTES);
     if (e != cudaSuccess) { set_cuda_error(e); return B200GNN_ERR_CUDA; }
-    attr_set = true;
+    attr_set[dev_a] = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   wgrad::Params p;

@@ -141,6 +141,63 @@ __global__ void __launch_bounds__(256) edge_sim_bwd_kernel(const float* __restri
   }
 }
 
+// Deterministic backward (replaces the atomic row adds above on the autograd path).  The gradient of node i is
+//     d f_i = sum_{e: dst=i} (w_e f[src_e] - sb_e f_i) + sum_{e: src=i} (w_e f[dst_e] - sa_e f_i)
+// i.e. ONE sparse product  d F = C · F  with the (2E + n)-entry matrix C that holds w_e at (dst_e, src_e) and
+// (src_e, dst_e) and  -(sum of the row's sa/sb)  on the diagonal.  The plan fixes C's CSR structure once per edge list
+// (pos_dst / pos_src / diag_pos = where each edge and each diagonal sits); every backward fills the values with the two
+// kernels below and runs the row-segmented SpMM (spmm.cu: fixed summation order, hub rows split) — bitwise repeatable.
+__global__ void __launch_bounds__(256) lsp_edge_coef_kernel(const float* __restrict__ feat, int F, const int32_t* __restrict__ src,
+                                                            const int32_t* __restrict__ dst, int64_t E, int kernel,
+                                                            const float* __restrict__ sim, const float* __restrict__ g,
+                                                            const int32_t* __restrict__ pos_dst, const int32_t* __restrict__ pos_src,
+                                                            float* __restrict__ val, float* __restrict__ selfc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t e = warp; e < E; e += nwarps) {
+    float ge = g[e];
+    float w, sa, sb;
+    if (kernel <= 1) {
+      const float* a = feat + (size_t)src[e] * F;
+      const float* b = feat + (size_t)dst[e] * F;
+      float dot = 0.f, na2 = 0.f, nb2 = 0.f;
+      for (int k = lane; k < F; k += 32) { const float x = __ldg(a + k), y = __ldg(b + k); dot = fmaf(x, y, dot); na2 = fmaf(x, x, na2); nb2 = fmaf(y, y, nb2); }
+      dot = wsum(dot); na2 = wsum(na2); nb2 = wsum(nb2);
+      const float ra = sqrtf(na2), rb = sqrtf(nb2);
+      const float na = fmaxf(ra, COS_EPS), nb = fmaxf(rb, COS_EPS);
+      const float c = dot / (na * nb);
+      if (kernel == 1) ge *= 2.f * c;
+      w = ge / (na * nb);
+      sa = ra > COS_EPS ? ge * c / (na * na) : 0.f;   // clamped norm carries no gradient
+      sb = rb > COS_EPS ? ge * c / (nb * nb) : 0.f;
+    } else {
+      float coef;  // d sim / d a = coef * (a - b),  d sim / d b = -coef * (a - b)
+      if (kernel == 2) { const float d = sim[e]; coef = d > 0.f ? ge / d : 0.f; }
+      else coef = -ge * sim[e];
+      w = -coef; sa = -coef; sb = -coef;
+    }
+    if (lane == 0) {
+      const int pd = pos_dst[e], ps = pos_src[e];
+      val[pd] = w; selfc[pd] = sb;
+      val[ps] = w; selfc[ps] = sa;
+    }
+  }
+}
+
+// val[diag_pos[i]] = -(sum of selfc over row i's off-diagonal entries, in CSR order); selfc[diag] is ignored.
+__global__ void __launch_bounds__(256) lsp_diag_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag_pos,
+                                                       int64_t n, const float* __restrict__ selfc, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int b = rowptr[i], e = rowptr[i + 1], dp = diag_pos[i];
+    float acc = 0.f;
+    for (int k = b + lane; k < e; k += 32) acc += (k == dp) ? 0.f : selfc[k];
+    acc = wsum(acc);                                  // xor-butterfly: the same tree every run
+    if (lane == 0) val[dp] = -acc;
+  }
+}
+
 static inline int edge_grid(int64_t items) {
   int64_t g = (items + 7) / 8;
   if (g > 148 * 16) g = 148 * 16;
@@ -181,5 +238,25 @@ extern "C" int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int3
   if (E == 0) return B200GNN_OK;
   if (!src || !dst) return B200GNN_ERR_BAD_ARG;
   edge_sim_bwd_kernel<<<edge_grid(E), 256, 0, (cudaStream_t)stream>>>(feat, (int)F, src, dst, E, kernel, sim, g, dfeat);
+  return check_launch();
+}
+
+// Values of the (2E + n)-entry backward matrix C (see lsp_edge_coef_kernel): the caller then runs
+// b200gnn_spmm_csr_f32(C, feat) to obtain d loss / d feat without atomics.
+extern "C" int b200gnn_lsp_bwd_values_f32(const float* feat, int64_t F, const int32_t* src, const int32_t* dst, int64_t E,
+                                          int kernel, const float* sim, const float* g, const int32_t* pos_dst,
+                                          const int32_t* pos_src, const int32_t* comb_rowptr, const int32_t* diag_pos,
+                                          int64_t n_nodes, float* val, float* selfc, void* stream) {
+  if (!feat || !sim || !g || !val || !selfc || !comb_rowptr || !diag_pos || F <= 0 || E < 0 || n_nodes <= 0 || kernel < 0 ||
+      kernel > 3)
+    return B200GNN_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (E > 0) {
+    if (!src || !dst || !pos_dst || !pos_src) return B200GNN_ERR_BAD_ARG;
+    lsp_edge_coef_kernel<<<edge_grid(E), 256, 0, st>>>(feat, (int)F, src, dst, E, kernel, sim, g, pos_dst, pos_src, val, selfc);
+    if ((rc = check_launch())) return rc;
+  }
+  lsp_diag_kernel<<<edge_grid(n_nodes), 256, 0, st>>>(comb_rowptr, diag_pos, n_nodes, selfc, val);
   return check_launch();
 }

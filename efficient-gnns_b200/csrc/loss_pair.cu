@@ -109,11 +109,14 @@ __global__ void __launch_bounds__(256) row_sqnorm_bwd_kernel(const float* __rest
 // ---------------------------------------------------------------- G-CRD rows: InfoNCE over Z = (fs_n ft_n^T) / tau
 // One CTA per row i of the S x S logits (already divided by tau through the operand scale):
 //   loss_i = logsumexp_j Z_ij - Z_ii ;   Z_ij <- (softmax_j(Z_i) - [i==j]) * w      (w = 1/S: d loss / d Z in place)
-__global__ void __launch_bounds__(256) nce_rows_kernel(float* __restrict__ Z, int S, float w, float* __restrict__ partial) {
+// Chunked form: Z holds rows [row_offset, row_offset + gridDim.x) of the S x S logits (row-major, S columns); the positive
+// of local row r is column row_offset + r.  partial is indexed by the GLOBAL row.
+__global__ void __launch_bounds__(256) nce_rows_kernel(float* __restrict__ Z, int S, float w, float* __restrict__ partial,
+                                                       int row_offset, int64_t ldz) {
   __shared__ float s_red[32];
   __shared__ float s_bc[2];
-  const int row = blockIdx.x;
-  float* z = Z + (size_t)row * S;
+  const int row = blockIdx.x + row_offset;
+  float* z = Z + (size_t)blockIdx.x * ldz;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float m = -INFINITY;
   for (int j = threadIdx.x; j < S; j += blockDim.x) m = fmaxf(m, z[j]);
@@ -306,9 +309,27 @@ extern "C" int b200gnn_nce_rows_f32(float* Z, int64_t S, float* loss_out, float*
   if (!Z || !loss_out || !partial || S <= 0 || S >= INT32_MAX) return B200GNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  nce_rows_kernel<<<(int)S, 256, 0, st>>>(Z, (int)S, 1.f / (float)S, partial);
+  nce_rows_kernel<<<(int)S, 256, 0, st>>>(Z, (int)S, 1.f / (float)S, partial, 0, S);
   if ((rc = check_launch())) return rc;
   sum_partials_kernel<<<1, 256, 0, st>>>(partial, (int)S, 1.0 / (double)S, loss_out);
+  return check_launch();
+}
+
+// Row chunk of the same pass: Z = rows [row_offset, row_offset + n_rows) of the S x S logits, row pitch ldz >= S floats
+// (columns S..ldz-1 are padding and are left untouched).
+// The S x S matrix never exists: the caller streams chunks small enough to stay in L2 (GEMM -> this pass -> the two
+// backward GEMMs), then b200gnn_nce_finish_f32 turns partial[S] into the loss.
+extern "C" int b200gnn_nce_rows_chunk_f32(float* Z, int64_t ldz, int64_t n_rows, int64_t S, int64_t row_offset, float* partial,
+                                          void* stream) {
+  if (!Z || !partial || S <= 0 || S >= INT32_MAX || ldz < S || n_rows <= 0 || row_offset < 0 || row_offset + n_rows > S)
+    return B200GNN_ERR_BAD_ARG;
+  nce_rows_kernel<<<(int)n_rows, 256, 0, (cudaStream_t)stream>>>(Z, (int)S, 1.f / (float)S, partial, (int)row_offset, ldz);
+  return check_launch();
+}
+
+extern "C" int b200gnn_nce_finish_f32(const float* partial, int64_t S, float* loss_out, void* stream) {
+  if (!partial || !loss_out || S <= 0 || S >= INT32_MAX) return B200GNN_ERR_BAD_ARG;
+  sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, (int)S, 1.0 / (double)S, loss_out);
   return check_launch();
 }
 

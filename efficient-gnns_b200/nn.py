@@ -409,7 +409,7 @@ class _GatAggregate(torch.autograd.Function):
     update_all, arxiv_dgl/models.py:202-217; PyG GATConv's message/aggregate) with its hand-written backward."""
 
     @staticmethod
-    def forward(ctx, ft, el, er, adj: SparseTensor, H: int, D: int, slope: float, eps: float):
+    def forward(ctx, ft, el, er, adj: SparseTensor, H: int, D: int, slope: float, eps: float, edge_keep=None, attn_scale=None):
         ft, el = ft.contiguous(), el.contiguous()
         er = None if er is None else er.contiguous()
         st = adj.storage
@@ -418,20 +418,24 @@ class _GatAggregate(torch.autograd.Function):
         n = G.n_rows
         a = torch.empty(G.nnz, H, dtype=torch.float32, device=ft.device)
         lib.check(L.b200gnn_gat_edge_softmax_f32(G.rowptr.data_ptr(), G.col.data_ptr(), el.data_ptr(),
-                                                 None if er is None else er.data_ptr(), n, H, slope, eps, a.data_ptr(), s),
+                                                 None if er is None else er.data_ptr(), n, H, slope, eps, a.data_ptr(),
+                                                 None if edge_keep is None else edge_keep.data_ptr(), s),
                   "gat_edge_softmax_f32")
+        a_used = a if attn_scale is None else a * attn_scale        # attention dropout (models.py:211-214)
         out = torch.empty(n, H * D, dtype=torch.float32, device=ft.device)
-        _gat_aggregate(G, None, a, ft, out, H, D)
+        _gat_aggregate(G, None, a_used, ft, out, H, D)
         ctx.adj, ctx.dims, ctx.slope = adj, (H, D), slope
-        ctx.save_for_backward(ft, el, er if er is not None else el, a)
-        ctx.has_er = er is not None
+        ctx.save_for_backward(ft, el, er if er is not None else el, a, a_used if attn_scale is not None else a,
+                              attn_scale if attn_scale is not None else a)
+        ctx.has_er, ctx.has_scale = er is not None, attn_scale is not None
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        ft, el, er, a = ctx.saved_tensors
+        ft, el, er, a, a_used, scale = ctx.saved_tensors
         H, D = ctx.dims
         er = er if ctx.has_er else None
+        scale = scale if ctx.has_scale else None
         dout = dout.contiguous()
         st = ctx.adj.storage
         G = st.engine_csr_unweighted() if st.value() is None else st.engine_csr()
@@ -442,16 +446,16 @@ class _GatAggregate(torch.autograd.Function):
                                              dout.data_ptr(), dout.stride(0), el.data_ptr(),
                                              None if er is None else er.data_ptr(), G.n_rows, H, D, ctx.slope, dpre.data_ptr(),
                                              None if der is None else der.data_ptr(), G.chunk_rowptr.data_ptr(), G.n_chunks,
-                                             *_hub_args(G, H), s),
+                                             *_hub_args(G, H), None if scale is None else scale.data_ptr(), s),
                   "gat_bwd_rows_f32")
         Gt = st.engine_csc("value")                              # transposed graph as CSR (rows = sources)
         perm = _csr2csc_i32(st)
         dft = torch.empty(Gt.n_rows, H * D, dtype=torch.float32, device=ft.device)
-        _gat_aggregate(Gt, perm, a, dout, dft, H, D)
+        _gat_aggregate(Gt, perm, a_used, dout, dft, H, D)
         d_el = torch.empty(Gt.n_rows, H, dtype=torch.float32, device=ft.device)
         lib.check(L.b200gnn_segment_sum_heads_f32(Gt.rowptr.data_ptr(), perm.data_ptr(), dpre.data_ptr(), Gt.n_rows, H,
                                                   d_el.data_ptr(), s), "segment_sum_heads_f32")
-        return dft, d_el, der, None, None, None, None, None
+        return dft, d_el, der, None, None, None, None, None, None, None
 
 
 def _csr2csc_i32(st) -> torch.Tensor:
@@ -476,21 +480,38 @@ def _hub_args(G, ws_width: int):
             G.hub_workspace(ws_width).data_ptr())
 
 
-def gat_aggregate(ft, el, er, adj: SparseTensor, heads: int, negative_slope: float = 0.2, softmax_eps: float = 0.0):
-    """ft [N, heads*D], el [N, heads], er [N_dst, heads] or None, adj rows = destinations -> [N_dst, heads*D]."""
-    return _GatAggregate.apply(ft, el, er, adj, heads, ft.shape[1] // heads, float(negative_slope), float(softmax_eps))
+def gat_aggregate(ft, el, er, adj: SparseTensor, heads: int, negative_slope: float = 0.2, softmax_eps: float = 0.0,
+                  edge_keep: Optional[torch.Tensor] = None, attn_scale: Optional[torch.Tensor] = None):
+    """ft [N, heads*D], el [N, heads], er [N_dst, heads] or None, adj rows = destinations -> [N_dst, heads*D].
+    edge_keep [nnz] uint8 (CSR order): dropped edges leave the softmax (edge_drop); attn_scale [nnz, heads] = keep/(1-p)
+    multiplies the attention coefficients after the softmax (attention dropout)."""
+    return _GatAggregate.apply(ft, el, er, adj, heads, ft.shape[1] // heads, float(negative_slope), float(softmax_eps),
+                               edge_keep, attn_scale)
+
+
+def _attention_masks(nnz: int, heads: int, edge_drop: float, attn_drop: float, training: bool, device):
+    """(edge_keep, attn_scale) of one training forward (arxiv_dgl/models.py:206-214): a random permutation drops the first
+    int(nnz*edge_drop) edges; nn.Dropout(attn_drop) on the coefficients.  torch's generator draws the decisions."""
+    keep = scale = None
+    if training and edge_drop > 0:
+        perm = torch.randperm(nnz, device=device)
+        keep = torch.ones(nnz, dtype=torch.uint8, device=device)
+        keep[perm[:int(nnz * edge_drop)]] = 0
+    if training and attn_drop > 0:
+        scale = (torch.rand(nnz, heads, device=device) >= attn_drop).float() / (1.0 - attn_drop)
+    return keep, scale
 
 
 class DGLGATConv(torch.nn.Module):
     """The reference's DGL GATConv (arxiv_dgl/models.py:95-236) on a SparseTensor adjacency (rows = destinations):
     same parameters (fc, attn_l, attn_r, res_fc), symmetric degree normalisation, optional residual / activation.
-    Stochastic edge/attention dropout of the teacher's training loop is not part of the distillation hot path."""
+    edge_drop / attn_drop (teacher training, models.py:206-214) are applied inside the fused kernels (edge keep-mask in the
+    softmax, coefficient scaling in the aggregation and its backward); the random draws come from torch's generator."""
 
     def __init__(self, in_feats, out_feats, num_heads=1, feat_drop=0.0, attn_drop=0.0, edge_drop=0.0, negative_slope=0.2,
                  use_attn_dst=True, residual=False, activation=None, allow_zero_in_degree=False, use_symmetric_norm=False):
         super().__init__()
-        if attn_drop > 0 or edge_drop > 0:
-            raise NotImplementedError("attention / edge dropout (teacher training only) is not implemented")
+        self.attn_drop_p, self.edge_drop = float(attn_drop), float(edge_drop)
         self._num_heads, self._out_feats, self._slope = num_heads, out_feats, negative_slope
         self._use_symmetric_norm, self._activation = use_symmetric_norm, activation
         self.fc = Linear(in_feats, out_feats * num_heads, bias=False)
@@ -520,7 +541,8 @@ class DGLGATConv(torch.nn.Module):
             ft = ft * out_deg.pow(-0.5).view(-1, 1, 1)
         el = (ft * self.attn_l).sum(-1)
         er = (ft_dst * self.attn_r).sum(-1) if self.attn_r is not None else None
-        rst = gat_aggregate(ft.reshape(-1, H * D), el, er, adj_t, H, self._slope, 0.0).view(-1, H, D)
+        keep, scale = _attention_masks(st.col().numel(), H, self.edge_drop, self.attn_drop_p, self.training, feat.device)
+        rst = gat_aggregate(ft.reshape(-1, H * D), el, er, adj_t, H, self._slope, 0.0, keep, scale).view(-1, H, D)
         if self._use_symmetric_norm:
             rst = rst * st.rowcount().float().clamp(min=1).pow(0.5).view(-1, 1, 1)
         if self.res_fc is not None:
@@ -535,8 +557,7 @@ class GATConv(torch.nn.Module):
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
                  bias=True, **kwargs):
         super().__init__()
-        if dropout > 0:
-            raise NotImplementedError("attention dropout is not implemented")
+        self.dropout = float(dropout)          # PyG: F.dropout on the attention coefficients in training
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
         self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
         self.lin_l = Linear(in_channels, heads * out_channels, bias=False)
@@ -559,7 +580,8 @@ class GATConv(torch.nn.Module):
             adj = adj.set_value(None).fill_diag(1.0) if adj.has_value() else _fill_diag_pattern(adj)
         xl = self.lin_l(x).view(-1, H, C)
         al, ar = (xl * self.att_l).sum(-1), (xl * self.att_r).sum(-1)
-        out = gat_aggregate(xl.reshape(-1, H * C), al, ar, adj, H, self.negative_slope, 1e-16).view(-1, H, C)
+        _, scale = _attention_masks(adj.storage.col().numel(), H, 0.0, self.dropout, self.training, x.device)
+        out = gat_aggregate(xl.reshape(-1, H * C), al, ar, adj, H, self.negative_slope, 1e-16, None, scale).view(-1, H, C)
         out = out.reshape(-1, H * C) if self.concat else out.mean(dim=1)
         return out if self.bias is None else out + self.bias
 

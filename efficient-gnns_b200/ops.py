@@ -229,16 +229,24 @@ def split_tf32(w: torch.Tensor, transpose: bool = False, hi: Optional[torch.Tens
 
 
 def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = a[M,K] @ b[N,K]^T (+bias) with fp32 fidelity on the tensor cores (b pre-split by split_tf32)."""
+                out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= a[M,K] @ b[N,K]^T (+bias) with fp32 fidelity on the tensor cores (b pre-split by split_tf32)."""
     M, K = a.shape
     N = b_hi.shape[0]
     assert b_hi.shape == b_lo.shape and b_hi.shape[1] == K
     if out is None:
+        assert not accumulate
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
-    lib.check(lib.load().b200gnn_gemm_tf32x3_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
-                                                 b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K,
-                                                 _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_f32")
+    L = lib.load()
+    if accumulate:
+        assert bias is None
+        lib.check(L.b200gnn_gemm_tf32x3_acc_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K, lib.stream_ptr()),
+                  "gemm_tf32x3_acc_f32")
+        return out
+    lib.check(L.b200gnn_gemm_tf32x3_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                        b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K,
+                                        _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_f32")
     return out
 
 

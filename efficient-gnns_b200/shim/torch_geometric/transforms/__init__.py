@@ -1,5 +1,5 @@
 """T.ToSparseTensor (arxiv_pyg/gnn.py:236-237)."""
-from efficient_gnns_b200.sparse import SparseTensor
+from efficient_gnns_b200.sparse import SparseTensor, device_argsort
 
 
 class ToSparseTensor:
@@ -9,7 +9,7 @@ class ToSparseTensor:
     def __call__(self, data):
         row, col = data.edge_index
         n = data.num_nodes
-        perm = (col * n + row).argsort()
+        perm = device_argsort(col, row, n, n)       # (col*n + row).argsort(): the device radix sort on CUDA inputs
         data.adj_t = SparseTensor(row=col[perm], col=row[perm], sparse_sizes=(n, n), is_sorted=True)
         if self.remove_edge_index:
             data.edge_index = None

@@ -119,6 +119,44 @@ def ptr2ind(ptr: torch.Tensor, nnz: int) -> torch.Tensor:
     return torch.repeat_interleave(torch.arange(counts.numel(), device=ptr.device), counts, output_size=nnz)
 
 
+# ----------------------------------------------------------------------------- device graph ingestion (csrc/graph_prep.cu)
+def _on_engine_device(*ts) -> bool:
+    return all(t is not None and t.is_cuda for t in ts)
+
+
+def device_argsort(major: torch.Tensor, minor: torch.Tensor, major_size: int, minor_size: int) -> torch.Tensor:
+    """Stable argsort of major*minor_size + minor: the hand-written radix sort on CUDA tensors (int64 in, int64 out, same
+    permutation as torch.argsort(stable=True)); torch on CPU tensors (host-side logic and its tests)."""
+    n = int(major.numel())
+    if n == 0 or not _on_engine_device(major, minor) or n >= 2 ** 31 - 1 or float(major_size) * float(minor_size) >= 1.8e19:
+        return torch.argsort(major * minor_size + minor, stable=True)
+    L = lib.load()
+    ws = torch.empty(int(L.b200gnn_graph_sort_workspace_bytes(n)), dtype=torch.uint8, device=major.device)
+    perm = torch.empty(n, dtype=torch.int32, device=major.device)
+    ma, mi = major.contiguous(), minor.contiguous()
+    lib.check(L.b200gnn_graph_argsort_i64(ma.data_ptr(), mi.data_ptr(), n, int(major_size), int(minor_size), perm.data_ptr(),
+                                          ws.data_ptr(), lib.stream_ptr()), "graph_argsort_i64")
+    return perm.long()
+
+
+def device_coalesce(row: torch.Tensor, col: torch.Tensor, n_rows: int, n_cols: int):
+    """(row, col, rowptr, src) of the row-sorted duplicate-free matrix (src = input index of each kept entry)."""
+    n = int(row.numel())
+    L = lib.load()
+    dev = row.device
+    ws = torch.empty(int(L.b200gnn_graph_sort_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    out_row, out_col = torch.empty(n, dtype=torch.long, device=dev), torch.empty(n, dtype=torch.long, device=dev)
+    src = torch.empty(n, dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n_rows + 1, dtype=torch.long, device=dev)
+    nnz = torch.zeros(1, dtype=torch.long, device=dev)
+    r, c = row.contiguous(), col.contiguous()
+    lib.check(L.b200gnn_graph_coalesce_i64(r.data_ptr(), c.data_ptr(), n, int(n_rows), int(n_cols), out_row.data_ptr(),
+                                           out_col.data_ptr(), src.data_ptr(), rowptr.data_ptr(), nnz.data_ptr(), ws.data_ptr(),
+                                           lib.stream_ptr()), "graph_coalesce_i64")
+    k = int(nnz.item())                       # one host read per graph (set-up time)
+    return out_row[:k], out_col[:k], rowptr, src[:k].long()
+
+
 class SparseStorage:
     """row-sorted COO/CSR storage with lazily cached derived arrays (shared by reference between views)."""
 
@@ -129,7 +167,7 @@ class SparseStorage:
         if not is_sorted and row.numel() > 1:
             key = row * N + col
             if not bool((key[1:] >= key[:-1]).all()):
-                perm = torch.argsort(key, stable=True)
+                perm = device_argsort(row, col, M, N)
                 row, col = row[perm], col[perm]
                 value = None if value is None else value[perm]
                 rowptr = None
@@ -160,8 +198,7 @@ class SparseStorage:
 
     def csr2csc(self):
         if self._csr2csc is None:
-            key = self._col * self._sizes[0] + self._row
-            self._csr2csc = torch.argsort(key, stable=True)
+            self._csr2csc = device_argsort(self._col, self._row, self._sizes[1], self._sizes[0])
         return self._csr2csc
 
     def colptr(self):
@@ -306,6 +343,10 @@ class SparseTensor:
         M, N = self.sparse_sizes()
         n = max(M, N)
         r2, c2 = torch.cat([row, col]), torch.cat([col, row])
+        if val is None and _on_engine_device(r2) and 0 < r2.numel() < 2 ** 31 - 1:
+            # sort + duplicate removal + row pointers in one pass of the ingestion kernels (csrc/graph_prep.cu)
+            ro, co, rowptr, _ = device_coalesce(r2, c2, n, n)
+            return SparseTensor(row=ro, rowptr=rowptr, col=co, sparse_sizes=(n, n), is_sorted=True)
         v2 = None if val is None else torch.cat([val, val])
         return SparseTensor(row=r2, col=c2, value=v2, sparse_sizes=(n, n), is_sorted=False).coalesce(reduce)
 

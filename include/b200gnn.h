@@ -244,6 +244,10 @@ int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
                             const float* B_lo, int64_t ldb, float* C,
                             int64_t ldc, int64_t M, int64_t N, int64_t K,
                             const float* bias, void* stream);
+/* C += A · B^T (accumulating epilogue; same operands as above, no bias). */
+int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
+                                int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                void* stream);
 
 /* Weight gradient  dW[Kin,Nout] = X[Nn,Kin]^T * G[Nn,Nout]  (GCNConv weight.grad / nn.Linear weight.grad^T),
  * split-K over the node index on tcgen05 (3xTF32), partials reduced in fixed order.
@@ -287,6 +291,12 @@ int b200gnn_row_sqnorm_bwd_f32(const float* x, const float* d_out, int64_t n,
 /* G-CRD / InfoNCE (nce_criterion :142-146) over logits Z[S,S] (already / tau):
  * loss_out[0] = mean_i(logsumexp_j Z_ij - Z_ii); Z is overwritten by d loss / d Z.  partial: float[S]. */
 int b200gnn_nce_rows_f32(float* Z, int64_t S, float* loss_out, float* partial, void* stream);
+/* The same pass on a ROW CHUNK of the logits (rows [row_offset, row_offset+n_rows), row pitch ldz >= S): the S x S
+ * matrix of criterion.py:142-146 is never materialised — the caller streams L2-sized chunks GEMM -> this pass -> the two
+ * backward GEMMs; b200gnn_nce_finish_f32 reduces partial[S] to the loss. */
+int b200gnn_nce_rows_chunk_f32(float* Z, int64_t ldz, int64_t n_rows, int64_t S, int64_t row_offset,
+                               float* partial, void* stream);
+int b200gnn_nce_finish_f32(const float* partial, int64_t S, float* loss_out, void* stream);
 int b200gnn_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 /* GSP (gpw_criterion :66-86): Gs/Gt = Gram matrices of the sampled student/teacher rows; kernel 0 cosine,
  * 1 poly, 2 l2, 3 rbf (ns/nt = row squared norms for 2,3).  loss_out[0] = mse(sim_s, sim_t); Gs is overwritten by
@@ -319,6 +329,16 @@ int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src,
                              const int32_t* dst, int64_t E, int kernel,
                              const float* sim, const float* g, float* dfeat,
                              void* stream);
+/* Deterministic LSP backward: d feat = C · feat with the (2E + n_nodes)-entry matrix C whose CSR structure
+ * (comb_rowptr, and per edge / per node the entry positions pos_dst, pos_src, diag_pos) the caller builds once per
+ * edge list: entry pos_dst[e] sits in row dst[e] at column src[e], pos_src[e] in row src[e] at column dst[e],
+ * diag_pos[i] at (i, i).  This call fills val[2E + n_nodes] (selfc is scratch of the same size); the product itself
+ * is b200gnn_spmm_csr_f32 — fixed summation order, no atomics (criterion.py:95-126 backward). */
+int b200gnn_lsp_bwd_values_f32(const float* feat, int64_t F, const int32_t* src, const int32_t* dst,
+                               int64_t E, int kernel, const float* sim, const float* g,
+                               const int32_t* pos_dst, const int32_t* pos_src,
+                               const int32_t* comb_rowptr, const int32_t* diag_pos, int64_t n_nodes,
+                               float* val, float* selfc, void* stream);
 
 /* ------------------------------------------------------------------ *
  * Graph attention (BASELINE config 4): per-destination edge softmax and
@@ -333,11 +353,14 @@ int b200gnn_edge_sim_bwd_f32(const float* feat, int64_t F, const int32_t* src,
  * H <= 16.  chunk_rowptr / hub_rows / hub_segptr: the plans of b200gnn_csr_chunk_plan / b200gnn_csr_hub_fill
  * (rows above hub_threshold are split into seg_len-edge segments, as in b200gnn_spmm_csr_f32).
  * hub_workspace: n_seg*H*D floats for gat_aggregate, n_seg*H floats for gat_bwd_rows (unused when n_hub == 0).
+ * Teacher-training knobs (arxiv_dgl/models.py:206-214): edge_keep [nnz] uint8 (NULL = keep all) — dropped edges get
+ * a = 0 and leave the softmax (edge_drop); attn_scale [nnz,H] (NULL = none) = keep/(1-p) of the attention dropout:
+ * the caller aggregates with a*attn_scale and gat_bwd_rows chains d a = d(a*attn_scale) * attn_scale.
  * ------------------------------------------------------------------ */
 int b200gnn_gat_edge_softmax_f32(const int32_t* rowptr, const int32_t* col,
                                  const float* el, const float* er, int64_t n_rows,
                                  int64_t H, float negative_slope, float softmax_eps,
-                                 float* a, void* stream);
+                                 float* a, const uint8_t* edge_keep, void* stream);
 int b200gnn_gat_aggregate_f32(const int32_t* rowptr, const int32_t* col,
                               const int32_t* eidx, const float* a, const float* ft,
                               int64_t ldf, float* out, int64_t ldo, int64_t n_rows,
@@ -355,7 +378,7 @@ int b200gnn_gat_bwd_rows_f32(const int32_t* rowptr, const int32_t* col, const fl
                              int32_t hub_threshold, int32_t seg_len,
                              const int32_t* hub_rows, const int32_t* hub_segptr,
                              int64_t n_hub, int64_t n_seg, float* hub_workspace,
-                             void* stream);
+                             const float* attn_scale, void* stream);
 int b200gnn_segment_sum_heads_f32(const int32_t* rowptr, const int32_t* eidx,
                                   const float* vals, int64_t n_rows, int64_t H,
                                   float* out, void* stream);
@@ -408,6 +431,25 @@ int b200gnn_typed_scatter_f32(const float* d_out, int64_t ldd, const int64_t* no
                               const int64_t* local_idx, const int64_t* order, int64_t n, int64_t F,
                               float* const* d_tables, const int64_t* table_rows, int32_t n_tables,
                               void* stream);
+
+/* ------------------------------------------------------------------
+ * Graph ingestion on the device — the integer half of the data path, bit-exact:
+ *   b200gnn_graph_argsort_i64  : perm = stable argsort of key = major*minor_size + minor.  ToSparseTensor
+ *                                (arxiv_pyg/gnn.py:236-237: major = edge_index[1], minor = edge_index[0]), an unsorted
+ *                                SparseTensor(row=, col=) (mag_pyg/gnn.py:151) and csr2csc (major = col, minor = row).
+ *   b200gnn_graph_coalesce_i64 : COO -> row-sorted duplicate-free COO + rowptr (to_symmetric's coalesce,
+ *                                arxiv_pyg/gnn.py:240).  out_row/out_col/src_out hold n entries, the first *nnz_out
+ *                                (device int64) are valid; src_out (nullable) = input index of each kept entry.
+ * Hand-written stable LSD radix sort (8-bit digits, only the digits the key range needs) + flags/scan/compaction +
+ * binary-search row pointers.  workspace: b200gnn_graph_sort_workspace_bytes(n) bytes, 256-byte aligned.
+ * n < 2^31; major_size*minor_size < 2^64.
+ * ------------------------------------------------------------------ */
+int64_t b200gnn_graph_sort_workspace_bytes(int64_t n);
+int b200gnn_graph_argsort_i64(const int64_t* major, const int64_t* minor, int64_t n, int64_t major_size,
+                              int64_t minor_size, int32_t* perm_out, void* workspace, void* stream);
+int b200gnn_graph_coalesce_i64(const int64_t* row, const int64_t* col, int64_t n, int64_t n_rows,
+                               int64_t n_cols, int64_t* out_row, int64_t* out_col, int32_t* src_out,
+                               int64_t* rowptr_out, int64_t* nnz_out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,3 +99,88 @@ def test_pyg_style_gatconv_adds_self_loops_and_concats():
     row, col = torch.cat([dst, loops]), torch.cat([src, loops])
     ref = onn.gat_aggregate(xl.reshape(n, H * C), (xl * al).sum(-1), (xl * ar).sum(-1), row, col, n, H, 0.2, 1e-16) + b
     assert rel_err(out, ref) < 1e-5
+
+
+def _dense_attention_ref(ft, el, er, row, col, n, H, D, slope, keep, scale):
+    """fp64 restatement of arxiv_dgl/models.py:202-217 with given edge keep-mask and attention-dropout scale (per edge)."""
+    e = torch.nn.functional.leaky_relu(el[col] + (er[row] if er is not None else 0), slope)        # [nnz, H]
+    if keep is not None:
+        e = e.masked_fill(~keep.bool().view(-1, 1), float("-inf"))
+    m = torch.full((n, H), float("-inf"), dtype=e.dtype).scatter_reduce_(0, row.view(-1, 1).expand_as(e), e.detach(), "amax")
+    m = torch.where(torch.isinf(m), torch.zeros_like(m), m)
+    ex = (e - m[row]).exp()
+    ssum = torch.zeros(n, H, dtype=e.dtype).index_add_(0, row, ex)
+    a = ex / ssum[row].clamp_min(1e-300)
+    if scale is not None:
+        a = a * scale
+    msg = ft.view(-1, H, D)[col] * a.unsqueeze(-1)
+    return torch.zeros(n, H, D, dtype=e.dtype).index_add_(0, row, msg).reshape(n, H * D)
+
+
+@pytest.mark.parametrize("H,D", [(3, 40), (8, 32)])
+def test_gat_edge_drop_and_attention_dropout_forward_backward(H, D):
+    """Teacher-training knobs of the reference's GATConv (arxiv_dgl/models.py:206-214) inside the fused kernels: a given edge
+    keep-mask (dropped edges leave the softmax; a destination may lose all its edges) and a given coefficient dropout."""
+    n = 3000
+    r, c = graph(n, 25_000, 3)
+    nnz = r.numel()
+    g = torch.Generator().manual_seed(H)
+    ft, el, er = torch.randn(n, H * D, generator=g), torch.randn(n, H, generator=g), torch.randn(n, H, generator=g)
+    w = torch.randn(n, H * D, generator=g)
+    keep = (torch.rand(nnz, generator=g) >= 0.3).to(torch.uint8)
+    keep[r == 11] = 0                                              # one destination loses every edge
+    scale = (torch.rand(nnz, H, generator=g) >= 0.25).float() / 0.75
+    ftr, elr, err = (t.double().requires_grad_(True) for t in (ft, el, er))
+    ref = _dense_attention_ref(ftr, elr, err, r, c, n, H, D, 0.2, keep, scale.double())
+    (ref * w.double()).sum().backward()
+    adj = SparseTensor(row=r.cuda(), col=c.cuda(), sparse_sizes=(n, n), is_sorted=True)
+    ftc, elc, erc = (t.cuda().requires_grad_(True) for t in (ft, el, er))
+    out = bnn.gat_aggregate(ftc, elc, erc, adj, H, 0.2, 0.0, keep.cuda(), scale.cuda())
+    (out * w.cuda()).sum().backward()
+    assert torch.count_nonzero(out[11]) == 0
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(ftc.grad, ftr.grad) < 2e-5 and rel_err(elc.grad, elr.grad) < 2e-5 and rel_err(erc.grad, err.grad) < 2e-5
+
+
+def test_dgl_gatconv_training_knobs_run_and_are_inert_in_eval():
+    n = 1200
+    r, c = graph(n, 8000, 4)
+    adj = SparseTensor(row=r.cuda(), col=c.cuda(), sparse_sizes=(n, n), is_sorted=True)
+    torch.manual_seed(0)
+    layer = bnn.DGLGATConv(32, 16, num_heads=3, attn_drop=0.1, edge_drop=0.2, residual=True, use_symmetric_norm=True).cuda()
+    plain = bnn.DGLGATConv(32, 16, num_heads=3, residual=True, use_symmetric_norm=True).cuda()
+    plain.load_state_dict(layer.state_dict())
+    x = torch.randn(n, 32).cuda().requires_grad_(True)
+    layer.train()
+    out = layer(adj, x)
+    out.sum().backward()
+    assert torch.isfinite(out).all() and torch.isfinite(x.grad).all()
+    layer.eval()
+    assert torch.equal(layer(adj, x), plain(adj, x))
+
+
+@pytest.mark.parametrize("concat", [True, False])
+def test_pyg_gatconv_gradients_and_head_mean(concat):
+    """PyG GATConv as ppi_pyg/gnn.py:27-31 uses it (heads 4/6, last layer concat=False): forward and every gradient
+    against the fp64 restatement (self-loops re-added, softmax eps 1e-16)."""
+    n, Fin, H, C = 700, 50, 4, 12
+    ei = skewed_edges(n, 4000, 5)
+    torch.manual_seed(2)
+    layer = bnn.GATConv(Fin, C, heads=H, concat=concat).cuda()
+    x = torch.randn(n, Fin)
+    w = torch.randn(n, H * C if concat else C)
+    xc = x.cuda().requires_grad_(True)
+    out = layer(xc, ei.cuda())
+    (out * w.cuda()).sum().backward()
+    W, al, ar, b = (p.detach().cpu().double().requires_grad_(True) for p in (layer.lin_l.weight, layer.att_l, layer.att_r, layer.bias))
+    xr = x.double().requires_grad_(True)
+    xl = (xr @ W.t()).view(n, H, C)
+    loops = torch.arange(n)
+    row, col = torch.cat([ei[1], loops]), torch.cat([ei[0], loops])
+    agg = onn.gat_aggregate(xl.reshape(n, H * C), (xl * al).sum(-1), (xl * ar).sum(-1), row, col, n, H, 0.2, 1e-16).view(n, H, C)
+    ref = (agg.reshape(n, H * C) if concat else agg.mean(1)) + b
+    (ref * w.double()).sum().backward()
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(xc.grad, xr.grad) < 5e-5
+    for p_, r_ in ((layer.lin_l.weight, W), (layer.att_l, al), (layer.att_r, ar), (layer.bias, b)):
+        assert rel_err(p_.grad, r_.grad) < 5e-5

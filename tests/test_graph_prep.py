@@ -73,3 +73,43 @@ def test_int32_narrowing_rejects_large_indices():
     from efficient_gnns_b200.sparse import _narrow_i32
     with pytest.raises(lib.B200GnnError):
         _narrow_i32(torch.tensor([0, 2 ** 31]), "col")
+
+
+# ---------------------------------------------------------------------------------------------- device ingestion kernels (f2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,major_size,minor_size", [(1, 5, 5), (31, 7, 3), (2049, 100, 100), (100_000, 169_343, 169_343),
+                                                     (300_000, 1_939_743, 1_939_743), (50_000, 3, 2 ** 40)])
+def test_device_radix_argsort_is_torch_stable_argsort(n, major_size, minor_size):
+    """b200gnn_graph_argsort_i64 (hand-written stable LSD radix sort) == torch.argsort(stable=True), duplicates included,
+    at tile boundaries, for MAG-sized ids (42-bit keys) and for a key range that needs 6 digit passes."""
+    from efficient_gnns_b200.sparse import device_argsort
+    g = torch.Generator().manual_seed(n)
+    major = torch.randint(0, major_size, (n,), generator=g)
+    minor = torch.randint(0, min(minor_size, 2 ** 62), (n,), generator=g)
+    major[n // 2:] = major[: n - n // 2]          # plenty of equal majors; equal keys too
+    minor[n // 3: n // 3 + n // 4] = minor[: n // 4]
+    want = torch.argsort(major * minor_size + minor, stable=True)
+    got = device_argsort(major.cuda(), minor.cuda(), major_size, minor_size)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,e,seed", [(1000, 6000, 1), (169_343, 1_166_243, 0)])
+def test_device_coalesce_matches_numpy_oracle(n, e, seed):
+    """to_symmetric through b200gnn_graph_coalesce_i64 at the real ARXIV size: rows, columns, row pointers and the source
+    index of every kept entry are bit-exact with oracle/graph.py."""
+    from efficient_gnns_b200.sparse import device_coalesce
+    ei = skewed_edges(n, e, seed)
+    r0, c0, _ = og.to_sparse_adj_t(ei.numpy(), n)
+    r1, c1 = og.to_symmetric(r0, c0, n)
+    rr = torch.cat([torch.from_numpy(r0), torch.from_numpy(c0)])
+    cc = torch.cat([torch.from_numpy(c0), torch.from_numpy(r0)])
+    ro, co, rowptr, src = device_coalesce(rr.cuda(), cc.cuda(), n, n)
+    assert np.array_equal(ro.cpu().numpy(), r1) and np.array_equal(co.cpu().numpy(), c1)
+    assert np.array_equal(rowptr.cpu().numpy(), og.ind2ptr(r1, n))
+    key = rr * n + cc
+    first = {}
+    order = torch.argsort(key, stable=True)
+    ks = key[order]
+    keep = torch.ones_like(ks, dtype=torch.bool); keep[1:] = ks[1:] != ks[:-1]
+    assert torch.equal(src.cpu(), order[keep])
