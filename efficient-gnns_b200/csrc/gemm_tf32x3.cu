@@ -44,8 +44,14 @@ struct Cfg {
   static constexpr int BN = BN_T, STAGES = NSTAGE;
   static constexpr int B_TILE_BYTES = BN_T * BK * 4;
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
-  static constexpr int ACC_STRIDE = BN_T <= 64 ? 64 : 128;                        // TMEM columns per accumulator
-  static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE;                       // 128 or 256 (power of two)
+  static constexpr int ACC_HALF = BN_T <= 64 ? 64 : 128;                          // TMEM columns of one accumulator
+  // Two accumulators per stage: [0, ACC_HALF) collects a_hi·b_hi, [ACC_HALF, 2·ACC_HALF) the two correction terms.
+  // The tensor core ROUNDS ITS fp32 ACCUMULATOR TOWARDS ZERO on every accumulate (tools/probe_accum.py: -2.7e-8 relative
+  // per MMA, i.e. -2.6e-6 after the 96 MMAs of a K=256 contraction, against 1e-7 for an fp32 FMA chain); the loss depends
+  // on how many times the LARGE accumulator is updated, not on what is added.  Keeping the 2^-11-sized correction terms
+  // in their own accumulator takes two of every three updates off the large one; the epilogue adds the pair (RN) once.
+  static constexpr int ACC_STRIDE = 2 * ACC_HALF;
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE;                       // 256 or 512 (power of two)
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // + slack for 1024 B alignment
   static_assert(B_TILE_BYTES % 1024 == 0 && BN_T % 16 == 0 && BN_T <= 256, "tile shape");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const Params p) {
   constexpr int BN = C::BN, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE_BYTES = C::B_TILE_BYTES;
-  constexpr int TMEM_COLS = C::TMEM_COLS, ACC_STRIDE = C::ACC_STRIDE;
+  constexpr int TMEM_COLS = C::TMEM_COLS, ACC_STRIDE = C::ACC_STRIDE, ACC_HALF = C::ACC_HALF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -151,9 +157,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t a_hi = make_smem_desc(st + koff), a_lo = make_smem_desc(st + TILE_BYTES + koff);
             const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES + koff);
             const uint64_t b_lo = make_smem_desc(st + 2 * TILE_BYTES + B_TILE_BYTES + koff);
-            mma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | k) != 0);
-            mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
-            mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
+            mma_tf32(d_tmem + ACC_HALF, a_lo, b_hi, idesc, (kb | k) != 0);   // correction accumulator
+            mma_tf32(d_tmem + ACC_HALF, a_hi, b_lo, idesc, 1);
+            mma_tf32(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);              // main accumulator
           }
           mma_commit(&empty[s]);                       // frees the smem stage once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -198,7 +204,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
       for (int c = 0; c < (BN + 31) / 32; ++c) {    // a partial last chunk reads spare columns of the accumulator's stride
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ACC_STRIDE + c * 32), r);
+        {
+          uint32_t rc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ACC_STRIDE + c * 32), r);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ACC_STRIDE + ACC_HALF + c * 32), rc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        }
         const int col0 = n0 + c * 32;
         if (vec_ok && col0 + 32 <= p.N) {
           // Transpose the warp's 32x32 block through shared memory so that global stores are whole 128-byte row

@@ -27,6 +27,15 @@ constexpr int OPER_BYTES = 8 * BKN * 128;     // 16 KB: up to 256 columns = 8 gr
 constexpr int STAGE_BYTES = 4 * OPER_BYTES;   // X_hi, X_lo, G_hi, G_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 512;
+// The tensor core rounds its fp32 accumulator towards zero on every accumulate (tools/probe_accum.py): a CTA that
+// chains its whole node range (~430 MMAs at ARXIV size) ends 1.3e-5 low; the loss depends on HOW OFTEN the large
+// accumulator is updated, not on what is added.  Two remedies, by TMEM budget:
+//   * the partial needs <= 256 columns (Kin = 128, or Nout <= 128): the two 2^-11-sized correction terms accumulate in
+//     their own TMEM region, which takes two of every three updates off the large accumulator; the epilogue adds the pair;
+//   * Kin = 256 with Nout > 128 fills all 512 columns: the chain is cut every DRAIN_KB node blocks instead — the epilogue
+//     adds the drained partial into the CTA's workspace slot with a rounded fp32 add and the next sub-range starts from
+//     a fresh accumulator (costs a pipeline bubble per drain, ~10 us; measured error 8.1e-6 -> 1.6e-6 at 16 blocks).
+constexpr int DRAIN_KB = 24;
 
 // MN-major tile [group][node][32 floats], 128B swizzle with 32-byte atoms
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
@@ -53,12 +62,14 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint64_t* split = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
   uint64_t* acc_full = bars + 3 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -75,6 +86,12 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int kb0 = (int)((int64_t)p.num_kb * blockIdx.x / gridDim.x);
   const int kb1 = (int)((int64_t)p.num_kb * (blockIdx.x + 1) / gridDim.x);
   const int mtiles = p.Kin / 128;
+  const int len = kb1 - kb0;
+  const bool sep = (mtiles == 1) || (p.Npad <= 128);   // room for a separate correction accumulator
+  const uint32_t corr_off = mtiles == 1 ? 256u : 128u;
+  int nd = sep ? 1 : (len + DRAIN_KB - 1) / DRAIN_KB;  // accumulator drains of this CTA (>= 1 when it has work)
+  if (nd < 1) nd = 1;
+  if (nd > len && len > 0) nd = len;
   const int xg = p.Kin / 32, gg = p.Npad / 32;               // 32-column groups of X and G
   const uint32_t tx_bytes = (uint32_t)(xg + gg) * BKN * 128;
 
@@ -96,28 +113,39 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int s = 0; uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[s], ph);
-        mbar_wait(&split[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+      for (int d = 0; d < nd; ++d) {
+        const int d0 = kb0 + (int)((int64_t)len * d / nd), d1 = kb0 + (int)((int64_t)len * (d + 1) / nd);
+        if (d > 0) { mbar_wait(acc_empty, (uint32_t)((d - 1) & 1)); tc_fence_after(); }   // previous partial drained
+        for (int kb = d0; kb < d1; ++kb) {
+          mbar_wait(&full[s], ph);
+          mbar_wait(&split[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
-        for (int kg = 0; kg < BKN / 8; ++kg) {
-          const uint64_t g_hi = make_desc_mn(st + 2 * OPER_BYTES + kg * 1024);
-          const uint64_t g_lo = make_desc_mn(st + 3 * OPER_BYTES + kg * 1024);
-          for (int mt = 0; mt < mtiles; ++mt) {
-            const uint32_t xoff = (uint32_t)(mt * 4 * BKN * 128 + kg * 1024);
-            const uint64_t x_hi = make_desc_mn(st + xoff), x_lo = make_desc_mn(st + OPER_BYTES + xoff);
-            const uint32_t d = tmem_base + (uint32_t)(mt * 256);
-            mma_tf32(d, x_lo, g_hi, idesc, (kb != kb0) | (kg != 0));
-            mma_tf32(d, x_hi, g_lo, idesc, 1);
-            mma_tf32(d, x_hi, g_hi, idesc, 1);
+          for (int kg = 0; kg < BKN / 8; ++kg) {
+            const uint64_t g_hi = make_desc_mn(st + 2 * OPER_BYTES + kg * 1024);
+            const uint64_t g_lo = make_desc_mn(st + 3 * OPER_BYTES + kg * 1024);
+            for (int mt = 0; mt < mtiles; ++mt) {
+              const uint32_t xoff = (uint32_t)(mt * 4 * BKN * 128 + kg * 1024);
+              const uint64_t x_hi = make_desc_mn(st + xoff), x_lo = make_desc_mn(st + OPER_BYTES + xoff);
+              const uint32_t dt = tmem_base + (uint32_t)(mt * 256);
+              const uint32_t first = (kb != d0) | (kg != 0);
+              if (sep) {
+                mma_tf32(dt + corr_off, x_lo, g_hi, idesc, first);
+                mma_tf32(dt + corr_off, x_hi, g_lo, idesc, 1);
+                mma_tf32(dt, x_hi, g_hi, idesc, first);
+              } else {
+                mma_tf32(dt, x_lo, g_hi, idesc, first);
+                mma_tf32(dt, x_hi, g_lo, idesc, 1);
+                mma_tf32(dt, x_hi, g_hi, idesc, 1);
+              }
+            }
           }
+          mma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        mma_commit(&empty[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        mma_commit(acc_full);
       }
-      mma_commit(acc_full);
     }
   } else if (warp >= 4 && warp < 8) {
     const int t = threadIdx.x - 128;
@@ -137,21 +165,34 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else if (warp >= 8) {
     const int q = warp & 3;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
     float* out = p.partial + (size_t)blockIdx.x * p.Kin * p.Npad;
-    for (int mt = 0; mt < mtiles; ++mt) {
-      const int row = mt * 128 + q * 32 + lane;
+    for (int d = 0; d < (len > 0 ? nd : 0); ++d) {
+      mbar_wait(acc_full, (uint32_t)(d & 1));
+      tc_fence_after();
+      for (int mt = 0; mt < mtiles; ++mt) {
+        const int row = mt * 128 + q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < gg; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + c * 32), r);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.Npad + c * 32);
+        for (int c = 0; c < gg; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + c * 32), r);
+          if (sep) {
+            uint32_t rc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + c * 32) + corr_off, rc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+          }
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)row * p.Npad + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            if (d > 0) { const float4 o = dst[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }   // same thread wrote it
+            dst[j] = v;
+          }
+        }
       }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
     }
   }
 

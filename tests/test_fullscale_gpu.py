@@ -62,5 +62,7 @@ def test_configs1_full_size_step_matches_fp64_oracle(arxiv, p):
     # arithmetic parity of the backward pass: same pattern => every gradient within 1e-5 in both norms
     assert max(pat["grad_max"]) <= 1e-5 and max(pat["grad_fro"]) <= 1e-5, pat
     assert max(pat["hidden_bias_abs_over_scale"]) <= 1e-5, pat
-    # free-running gradients: Frobenius bound (each flip moves single entries of dW by O(1/N) of its scale)
-    assert max(free["grad_fro"]) <= 1e-4, free
+    # free-running gradients: one flipped hidden unit of node i moves the 128 entries dW0[:, k] by |AX_i|*|dY_ik| each, which
+    # is ~1.5e-4 of ||dW0||_F at this size (sqrt(128) against sqrt(N*128*256) random-sign terms; measured: p=0: 3 flips ->
+    # 1.6e-4, p=0.5 (kept units weigh 2x, half as many terms): 2 flips -> 7.4e-4), so the bound scales with the flip count
+    assert max(free["grad_fro"]) <= 5e-4 * max(1, sum(free["flips"])), free

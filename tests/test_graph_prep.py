@@ -86,8 +86,8 @@ def test_device_radix_argsort_is_torch_stable_argsort(n, major_size, minor_size)
     g = torch.Generator().manual_seed(n)
     major = torch.randint(0, major_size, (n,), generator=g)
     minor = torch.randint(0, min(minor_size, 2 ** 62), (n,), generator=g)
-    major[n // 2:] = major[: n - n // 2]          # plenty of equal majors; equal keys too
-    minor[n // 3: n // 3 + n // 4] = minor[: n // 4]
+    major[n // 2:] = major[: n - n // 2].clone()  # plenty of equal majors; equal keys too
+    minor[n // 3: n // 3 + n // 4] = minor[: n // 4].clone()
     want = torch.argsort(major * minor_size + minor, stable=True)
     got = device_argsort(major.cuda(), minor.cuda(), major_size, minor_size)
     assert got.dtype == torch.int64 and torch.equal(got.cpu(), want)

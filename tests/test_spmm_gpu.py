@@ -171,8 +171,9 @@ def test_large_arxiv_shape_properties():
 
 # ---------------------------------------------------------------------------------------------- round 2: bulk-copy kernel
 # variant word: 2 = cp.async ring, 3 = bulk (slab min(K,256)), 4 = bulk 128-float slabs, 5 = bulk 256-float slabs,
-# +16 evict_last gathers, +32 other barrier-group size (efficient-gnns_b200/csrc/spmm.cu)
-BULK_VARIANTS = [0, 1, 2, 3, 4, 5, 3 + 16, 4 + 16, 3 + 32, 4 + 32, 5 + 16 + 32]
+# 6 / 7 = TMA gather4 quads over 128-float slabs (8 / 4 edges per barrier), +16 evict_last gathers, +32 other barrier-group
+# size, +64 two CTAs per SM (efficient-gnns_b200/csrc/spmm.cu)
+BULK_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 3 + 16, 4 + 16, 3 + 32, 4 + 32, 5 + 16 + 32, 3 + 64]
 
 
 @pytest.fixture
@@ -216,7 +217,7 @@ def test_spmm_bulk_variants_hubs_stats_bias(K, variant, spmm_variant):
     assert rel_err(outm[7], refm[7]) < TOL and rel_err(outm[4000], refm[4000]) < TOL
 
 
-@pytest.mark.parametrize("variant", [3, 4, 4 + 16])
+@pytest.mark.parametrize("variant", [3, 4, 4 + 16, 6, 7])
 def test_spmm_bulk_tiny_and_ragged(variant, spmm_variant):
     """Degenerate shapes on the bulk kernel: a single edge, rows of degree exactly G / ring depth, a graph smaller than one
     chunk, and a rectangular matrix whose sources are never referenced beyond n_src."""
