@@ -238,8 +238,7 @@ class ShardedGCNTrainer(GCNStudentTrainer):
         ops.kd_loss_fwd_bwd(logits, y_loc, train_loc, teacher_loc, self.alpha, self.kd_T, d_logits=self.dY[-1],
                             loss_out=self.loss_out, partial=self.kd_part, n_norm=self.n_train_global)
         self.backward(x_pad)
-        dist.all_reduce(self.grads, group=self.group)
-        dist.all_reduce(self.loss_out, group=self.group)
+        dist.all_reduce(self._grads_buf, group=self.group)      # gradients + the three loss scalars
         ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr)
 
     def exchange_bytes_per_step(self) -> int:

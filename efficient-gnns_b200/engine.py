@@ -90,7 +90,11 @@ class GCNStudentTrainer:
         n_par = sum(sizes)
         dev = self.device
         self.params = torch.zeros(n_par, device=dev)
-        self.grads = torch.zeros(n_par, device=dev)
+        # gradients and the three loss scalars share one buffer (padded to 16 bytes): the multi-GPU engines exchange and
+        # reduce both with a single launch
+        self.n_par_pad = (n_par + 3) // 4 * 4
+        self._grads_buf = torch.zeros(self.n_par_pad + 4, device=dev)
+        self.grads = self._grads_buf[:n_par]
         self.exp_avg = torch.zeros(n_par, device=dev)
         self.exp_avg_sq = torch.zeros(n_par, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -144,7 +148,7 @@ class GCNStudentTrainer:
         self.stat_part = [torch.empty(slots_spmm, 2, dims[l + 1], device=dev) for l in range(self.L - 1)]
         self.bn = [torch.empty(4, dims[l + 1], device=dev) for l in range(self.L - 1)]   # mean, invstd, scale, shift
         self.rs = ops.rows_slots(N)
-        self.loss_out = torch.zeros(3, device=dev)
+        self.loss_out = self._grads_buf[self.n_par_pad:self.n_par_pad + 3]
         self.kd_part = torch.empty(2 * int(lib.load().b200gnn_kd_partials(N)), device=dev)
         self._graph = None
         # weight gradients only feed Adam: they run on a side stream next to the BN/ReLU backward passes and the next

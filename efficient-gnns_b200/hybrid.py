@@ -131,6 +131,16 @@ class TorchExchange:
         pass
 
 
+class NullExchange(TorchExchange):
+    """TIMING DIAGNOSTICS ONLY: one rank's share of the compute on a single GPU, exchanges skipped (results are wrong).
+    Lets ncu profile what a rank of a P-GPU run executes (ncu must not wrap multi-rank commands)."""
+
+    def r2c(self, src, dst, name=""): pass
+    def c2r(self, src, dst, name=""): pass
+    def allgather_rows(self, src, dst, name=""): pass
+    def allgather_vec(self, src, dst, name=""): pass
+
+
 class PeerExchange:
     """The same primitives as direct stores into the consumers' buffers (CUDA IPC arena + flag barrier)."""
 
@@ -150,8 +160,7 @@ class PeerExchange:
         kc = K // P
         off = self.plan.offsets[self.rank]
         copies = [(self.arena.peer_ptr(name, q, off * kc), src.data_ptr() + 4 * q * kc, kc, src.stride(0), n_p) for q in self._order]
-        copy2d(copies, kc)
-        self.arena.barrier()
+        self.arena.exchange(copies, kc)
 
     def c2r(self, src: torch.Tensor, dst: torch.Tensor, name: str):
         from .peer import copy2d
@@ -159,24 +168,21 @@ class PeerExchange:
         K = kc * P
         copies = [(self.arena.peer_ptr(name, q, self.rank * kc), src.data_ptr() + 4 * self.plan.offsets[q] * src.stride(0), K,
                    src.stride(0), self.plan.counts[q]) for q in self._order]
-        copy2d(copies, kc)
-        self.arena.barrier()
+        self.arena.exchange(copies, kc)
 
     def allgather_rows(self, src: torch.Tensor, dst: torch.Tensor, name: str):
         from .peer import copy2d
         K = src.shape[1]
         off = self.plan.offsets[self.rank]
         copies = [(self.arena.peer_ptr(name, q, off * K), src.data_ptr(), K, src.stride(0), self.n_p) for q in self._order]
-        copy2d(copies, K)
-        self.arena.barrier()
+        self.arena.exchange(copies, K)
 
     def allgather_vec(self, src: torch.Tensor, dst: torch.Tensor, name: str):
         from .peer import copy2d
         m = src.numel()
         assert m % 4 == 0
         copies = [(self.arena.peer_ptr(name, q, self.rank * m), src.data_ptr(), m, m, 1) for q in self._order]
-        copy2d(copies, m)
-        self.arena.barrier()
+        self.arena.exchange(copies, m)
 
     def check(self):
         if self.arena.error_flag():
@@ -194,10 +200,14 @@ def _numel(shape) -> int:
 class HybridGCNTrainer(GCNStudentTrainer):
     """One rank of the hybrid-layout GCN student; same step semantics as GCNStudentTrainer (engine.py)."""
 
-    def __init__(self, adj: SparseTensor, dims: List[int], group=None, exchange: str = "peer", **kw):
-        assert dist.is_initialized(), "torch.distributed must be initialised"
+    def __init__(self, adj: SparseTensor, dims: List[int], group=None, exchange: str = "peer", _fake=None, **kw):
         self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if _fake is not None:                       # (rank, world) of a pretended run: exchange="null" only
+            assert exchange == "null"
+            self.rank, self.world = _fake
+        else:
+            assert dist.is_initialized(), "torch.distributed must be initialised"
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         P = self.world
         norm = gcn_norm(adj)
         if not _is_symmetric(norm):
@@ -219,8 +229,8 @@ class HybridGCNTrainer(GCNStudentTrainer):
         # aggregation mode per operand width
         self.col_mode = {k: (k % (4 * P) == 0) for k in set(dims)}
         n_par = self.params.numel()
-        n_par_pad = (n_par + 3) // 4 * 4
         self.n_par = n_par
+        n_red = self._grads_buf.numel()                 # gradients + loss scalars, reduced together
         B = self.plan.block
         kin = dims[0]
         # ---- buffers: ("ex", ...) are destinations of exchanges (peer stores land in them: they live in the arena),
@@ -244,9 +254,14 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 specs += [("ex", f"Hfull{l}", (N, k)), ("ex", f"dYfull{l}", (N, k))]
         for k in sorted(set(dims[1:-1])):
             specs.append(("ex", f"stat_all{k}", (P, 2, k)))
-        specs += [("ex", "grads_all", (P, n_par_pad)), ("ex", "loss_all", (P, 4))]
+        specs += [("ex", "grads_all", (P, n_red))]
         need = sum((4 * _numel(shape) + 255) // 256 * 256 for kind, _, shape in specs if kind == "ex") + 4096
-        self.ex = PeerExchange(self.plan, self.rank, need, group) if exchange == "peer" else TorchExchange(self.plan, self.rank, group)
+        if exchange == "peer":
+            self.ex = PeerExchange(self.plan, self.rank, need, group)
+        elif exchange == "null":
+            self.ex = NullExchange(self.plan, self.rank, group)
+        else:
+            self.ex = TorchExchange(self.plan, self.rank, group)
         self.c: Dict[str, torch.Tensor] = {}
         for kind, name, shape in specs:
             t = self.ex.buffer(name, shape, dev) if kind == "ex" else torch.zeros(*shape, device=dev)
@@ -256,9 +271,7 @@ class HybridGCNTrainer(GCNStudentTrainer):
         kmax = max(dims[1:])
         self.stat_loc = torch.zeros(2 * kmax, device=dev)
         self.stat_all = {k: self.c[f"stat_all{k}"] for k in set(dims[1:-1])}
-        self.grads_all, self.loss_all = self.c["grads_all"], self.c["loss_all"]
-        self.grads_pad = torch.zeros(n_par_pad, device=dev)
-        self.loss4 = torch.zeros(4, device=dev)
+        self.grads_all = self.c["grads_all"]
         self.bn_c = {l: torch.empty(4, dims[l + 1] // P, device=dev) for l in range(L - 1) if self.col_mode[dims[l + 1]]}
         slots_full = ops.stat_slots(self.Gfull)
         self.stat_part_c = {l: torch.empty(slots_full, 2, dims[l + 1] // P, device=dev)
@@ -358,8 +371,12 @@ class HybridGCNTrainer(GCNStudentTrainer):
                     self.ex.c2r(c[f"Yc{l}"], c[f"Y_R{l}"], f"Y_R{l}")
                     return c[f"Y_R{l}"]
                 if training:
-                    part = self.stat_part_c[l]
-                    ops.spmm_csr(self.Gfull, c[f"Hc{l}"], "sum", bias=bias_c, out=c[f"Yc{l}"], stat_partial=part)
+                    if kc <= 64:      # narrow slices: the multi-row-per-warp kernel (no fused statistics) + one small pass
+                        ops.spmm_csr(self.Gfull, c[f"Hc{l}"], "sum", bias=bias_c, out=c[f"Yc{l}"])
+                        part = ops.col_stats(c[f"Yc{l}"], partial=self._part_c(kc))
+                    else:
+                        part = self.stat_part_c[l]
+                        ops.spmm_csr(self.Gfull, c[f"Hc{l}"], "sum", bias=bias_c, out=c[f"Yc{l}"], stat_partial=part)
                     ops.bn_finalize(part, self.n_global, self._cols(self.gamma[l], k), self._cols(self.beta[l], k), self.bn_eps,
                                     self.bn_momentum, self._cols(self.running_mean[l], k), self._cols(self.running_var[l], k),
                                     out=self.bn_c[l])
@@ -406,6 +423,7 @@ class HybridGCNTrainer(GCNStudentTrainer):
         (summed over ranks by the caller).  Parameters whose gradient a rank computes from whole columns
         (feature-parallel BatchNorm: gamma/beta/conv-bias slices) are zero outside its slice."""
         c, P, dims, L = self.c, self.world, self.dims, self.L
+        self.grads.zero_()                              # slices a rank does not own stay zero (summed over ranks later)
         d_act = None                                    # d loss / d A_{l-1} in R layout, produced by layer l's dgrad
         for l in range(L - 1, -1, -1):
             k = dims[l + 1]
@@ -432,7 +450,6 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 else:
                     self.ex.r2c(d_act, c[f"dAc{l}"], f"dAc{l}")
                     bn = self.bn_c[l]
-                    self.ggamma[l].zero_(); self.gbeta[l].zero_(); self.gb[l].zero_()
                     pk = self._part_c(kc)
                     ops.bn_act_bwd(c[f"dAc{l}"], c[f"Ac{l}"], c[f"Yc{l}"], bn[0], bn[1], self._cols(self.gamma[l], k), self.p,
                                    d_y=c[f"dYc{l}"], d_gamma=self._cols(self.ggamma[l], k), d_beta=self._cols(self.gbeta[l], k),
@@ -473,16 +490,10 @@ class HybridGCNTrainer(GCNStudentTrainer):
         ops.kd_loss_fwd_bwd(logits, y_loc, train_loc, teacher_loc, self.alpha, self.kd_T, d_logits=self.dY[-1],
                             loss_out=self.loss_out, partial=self.kd_part, n_norm=self.n_train_global)
         self.backward(x_in)
-        # gradients and loss scalars: every rank's contribution lands in every rank's [P, n] buffer and is summed in
-        # rank order (fp64) -> bit-identical replicas, no all-reduce
-        self.grads_pad[:self.n_par].copy_(self.grads)
-        self.ex.allgather_vec(self.grads_pad, self.grads_all, "grads_all")
-        ops.partial_reduce(self.grads_all, out=self.grads_pad)
-        self.grads.copy_(self.grads_pad[:self.n_par])
-        self.loss4[:3].copy_(self.loss_out)
-        self.ex.allgather_vec(self.loss4, self.loss_all, "loss_all")
-        ops.partial_reduce(self.loss_all, out=self.loss4)
-        self.loss_out.copy_(self.loss4[:3])
+        # gradients and loss scalars (one buffer): every rank's contribution lands in every rank's [P, n] block and is summed
+        # in rank order (fp64) -> bit-identical replicas, no all-reduce
+        self.ex.allgather_vec(self._grads_buf, self.grads_all, "grads_all")
+        ops.partial_reduce(self.grads_all, out=self._grads_buf)
         ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr)
 
     def exchange_bytes_per_step(self) -> int:

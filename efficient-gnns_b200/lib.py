@@ -104,6 +104,7 @@ SIGNATURES = {
     "b200gnn_ipc_close_handle": (_int, [_ptr]),
     "b200gnn_peer_copy2d_f32": (_int, [_ptr, _i32, _i64, _ptr]),
     "b200gnn_peer_barrier": (_int, [_ptr, _i32, _i32, _ptr, _ptr, _ptr]),
+    "b200gnn_peer_exchange_f32": (_int, [_ptr, _i32, _i64, _ptr, _i32, _i32, _ptr, _ptr, _ptr, _ptr]),
 }
 
 

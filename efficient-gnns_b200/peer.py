@@ -67,6 +67,7 @@ class PeerArena:
         self._flag_ptrs = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self.peer_base])
         self._epoch_ptr = self.base + 128
         self._error_ptr = self.base + 136
+        self._ticket_ptr = self.base + 144
         self.buffers: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         dist.barrier(group=group)
 
@@ -90,6 +91,18 @@ class PeerArena:
     def barrier(self):
         lib.check(lib.load().b200gnn_peer_barrier(self._flag_ptrs, self.rank, self.world, C.c_void_p(self._epoch_ptr),
                                                   C.c_void_p(self._error_ptr), lib.stream_ptr()), "peer_barrier")
+
+    def exchange(self, copies, width: int):
+        """The copies (dst_ptr, src_ptr, ld_dst, ld_src, rows) and the flag barrier in ONE launch (<= 16 copies)."""
+        if len(copies) > 16:
+            copy2d(copies, width)
+            return self.barrier()
+        arr = (lib.Copy2D * max(len(copies), 1))()
+        for j, (d, s, ldd, lds, rows) in enumerate(copies):
+            arr[j].dst, arr[j].src, arr[j].ld_dst, arr[j].ld_src, arr[j].rows = d, s, ldd, lds, rows
+        lib.check(lib.load().b200gnn_peer_exchange_f32(arr, len(copies), int(width), self._flag_ptrs, self.rank, self.world,
+                                                       C.c_void_p(self._epoch_ptr), C.c_void_p(self._error_ptr),
+                                                       C.c_void_p(self._ticket_ptr), lib.stream_ptr()), "peer_exchange_f32")
 
     def error_flag(self) -> int:
         return int(self._mem[136:140].view(torch.int32).item())

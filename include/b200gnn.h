@@ -413,6 +413,11 @@ int b200gnn_ipc_close_handle(void* ptr);
 int b200gnn_peer_copy2d_f32(const b200gnn_copy2d* copies, int32_t n, int64_t width, void* stream);
 int b200gnn_peer_barrier(uint64_t* const* peer_flags, int32_t rank, int32_t world,
                          uint64_t* epoch, int32_t* error, void* stream);
+/* copy2d + barrier in ONE launch: the CTA that finishes last (ticket: device uint32, zero-initialised, re-armed by the
+ * kernel) runs the flag barrier, so the kernel ends when every rank's blocks have been exchanged. */
+int b200gnn_peer_exchange_f32(const b200gnn_copy2d* copies, int32_t n, int64_t width,
+                              uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* epoch,
+                              int32_t* error, uint32_t* ticket, void* stream);
 
 /* ------------------------------------------------------------------
  * Heterogeneous input assembly — RGCN.group_input, mag_pyg/gnn.py:111-124 (called from RGCN.forward :126-129):
