@@ -186,12 +186,27 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_kernel(const float* _
 // local columns [4*cv_off, 4*cv_off + 4*nvec_l) of a matrix that is nvec_g float4 wide globally.  The keep decision of
 // an element is the one affine_relu_dropout_kernel takes for the same (node, feature) of the full matrix, so any
 // row/column sharding and any node relabelling of the node-parallel engine reproduces the single-GPU mask bit for bit.
+// Optional second destination of the block pass: the fused C->R layout exchange (hybrid.py) — row r of this [n_rows, K]
+// block belongs to the rank q with off[q] <= r < off[q+1] and is ALSO stored to ptr[q] + (r - off[q]) * ld + col.
+struct RowScatter {
+  float* ptr[16];
+  int32_t off[17];
+  int32_t n;
+  int64_t ld, col;
+};
+__device__ __forceinline__ float* scatter_row(const RowScatter& sc, int64_t r) {
+  int q = 0;
+#pragma unroll 1
+  while (q + 1 < sc.n && r >= sc.off[q + 1]) ++q;
+  return sc.ptr[q] + (size_t)(r - sc.off[q]) * (size_t)sc.ld + sc.col;
+}
+
 template <bool P16>
 __global__ void __launch_bounds__(256) affine_relu_dropout_mapped_kernel(
     const float* __restrict__ Y, float* __restrict__ out, int64_t n_rows, int nvec_l, const float* __restrict__ scale,
     const float* __restrict__ shift, int relu, float p, uint32_t thr16, uint64_t seed, uint64_t offset,
     const int32_t* __restrict__ step_dev, uint64_t step_mul, const int32_t* __restrict__ rowmap, uint64_t row_offset,
-    uint64_t nvec_g, uint64_t cv_off, int paired) {
+    uint64_t nvec_g, uint64_t cv_off, int paired, const RowScatter sc) {
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (step_dev) offset += (uint64_t)(*step_dev) * step_mul;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -211,6 +226,7 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_mapped_kernel(
         y.x = m.x ? y.x * inv_keep : 0.f; y.y = m.y ? y.y * inv_keep : 0.f;
         y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
         st4(out + 4 * i, y);
+        if (sc.n) st4(scatter_row(sc, r) + 4 * (cv + half), y);
       }
     }
     return;
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(256) affine_relu_dropout_mapped_kernel(
       y.z = m.z ? y.z * inv_keep : 0.f; y.w = m.w ? y.w * inv_keep : 0.f;
     }
     st4(out + 4 * i, y);
+    if (sc.n) st4(scatter_row(sc, r) + 4 * cv, y);
   }
 }
 
@@ -434,11 +451,9 @@ extern "C" int b200gnn_affine_relu_dropout_f32(const float* Y, float* out, int64
 
 // Block form of the pass above (node-parallel engine): rows are nodes rowmap[r] (or r + row_offset), columns are
 // [col_offset, col_offset + K) of a K_global-wide activation matrix; masks equal the single-GPU ones elementwise.
-extern "C" int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
-                                                      const float* scale, const float* shift, int relu, float p,
-                                                      uint64_t seed, uint64_t offset, const int32_t* step_dev,
-                                                      uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
-                                                      int64_t K_global, int64_t col_offset, void* stream) {
+static int mapped_launch(const float* Y, float* out, int64_t n_rows, int64_t K, const float* scale, const float* shift, int relu,
+                         float p, uint64_t seed, uint64_t offset, const int32_t* step_dev, uint64_t step_mul, const int32_t* rowmap,
+                         uint64_t row_offset, int64_t K_global, int64_t col_offset, const RowScatter& sc, void* stream) {
   if (!rows_ok(n_rows, K) || !Y || !out || p < 0.f || p >= 1.f || ((scale == nullptr) != (shift == nullptr)) ||
       !aligned_to(Y, 16) || !aligned_to(out, 16) || K_global < K || K_global % 4 || col_offset < 0 || col_offset % 4 ||
       col_offset + K > K_global)
@@ -452,12 +467,47 @@ extern "C" int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out
   if (dropout_p16(p, thr16))
     affine_relu_dropout_mapped_kernel<true><<<grid_for(paired ? n_vec / 2 : n_vec, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
         Y, out, n_rows, nvec_l, scale, shift, relu, p, thr16, seed, offset, step_dev, step_mul, rowmap, row_offset, nvec_g,
-        cv_off, paired);
+        cv_off, paired, sc);
   else
     affine_relu_dropout_mapped_kernel<false><<<grid_for(n_vec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
         Y, out, n_rows, nvec_l, scale, shift, relu, p, 0u, seed, offset, step_dev, step_mul, rowmap, row_offset, nvec_g,
-        cv_off, 0);
+        cv_off, 0, sc);
   return check_launch();
+}
+
+// Block form of the pass above (node-parallel engine): rows are nodes rowmap[r] (or r + row_offset), columns are
+// [col_offset, col_offset + K) of a K_global-wide activation matrix; masks equal the single-GPU ones elementwise.
+extern "C" int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                                      const float* scale, const float* shift, int relu, float p,
+                                                      uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                                                      uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
+                                                      int64_t K_global, int64_t col_offset, void* stream) {
+  RowScatter sc;
+  sc.n = 0; sc.ld = 0; sc.col = 0;
+  return mapped_launch(Y, out, n_rows, K, scale, shift, relu, p, seed, offset, step_dev, step_mul, rowmap, row_offset, K_global,
+                       col_offset, sc, stream);
+}
+
+// ... and with the C->R layout exchange fused: every output row is ALSO stored to the R-layout buffer of the rank that owns
+// the node (dst_ptrs[q] + (r - row_off[q]) * ld_dst + col_offset; HOST arrays, peer-mapped pointers).
+extern "C" int b200gnn_affine_relu_dropout_scatter_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                                       const float* scale, const float* shift, int relu, float p,
+                                                       uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                                                       uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
+                                                       int64_t K_global, int64_t col_offset, float* const* dst_ptrs,
+                                                       const int32_t* row_off, int32_t world, int64_t ld_dst, void* stream) {
+  if (!dst_ptrs || !row_off || world <= 0 || world > 16 || ld_dst < K_global || ld_dst % 4 || row_off[0] != 0 ||
+      row_off[world] != n_rows)
+    return B200GNN_ERR_BAD_ARG;
+  RowScatter sc;
+  sc.n = world; sc.ld = ld_dst; sc.col = col_offset;
+  for (int q = 0; q < world; ++q) {
+    if (!dst_ptrs[q] || !aligned_to(dst_ptrs[q], 16) || row_off[q + 1] < row_off[q]) return B200GNN_ERR_BAD_ARG;
+    sc.ptr[q] = dst_ptrs[q]; sc.off[q] = row_off[q];
+  }
+  sc.off[world] = row_off[world];
+  return mapped_launch(Y, out, n_rows, K, scale, shift, relu, p, seed, offset, step_dev, step_mul, rowmap, row_offset, K_global,
+                       col_offset, sc, stream);
 }
 
 extern "C" int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p, uint64_t seed,

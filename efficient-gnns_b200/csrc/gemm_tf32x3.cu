@@ -80,6 +80,12 @@ struct Params {
   int64_t ldc;
   int32_t M, N, K;
   int32_t accumulate;   // C += A·B^T (+bias) instead of C = ...
+  // Fused R->C layout exchange of the multi-GPU engine (hybrid.py): output columns [q*kc, (q+1)*kc) go to rank q's
+  // [N, kc] buffer Cp[q] at rows row_off + m — the epilogue stores straight into the consumers' memory over NVLink
+  // (peer mappings), so the exchange costs no kernel of its own and overlaps the GEMM tile by tile.  n_peer = 0: off.
+  float* Cp[16];
+  int32_t n_peer, kc;
+  int64_t row_off;
 };
 
 template <class C>
@@ -195,7 +201,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     int a = 0; uint32_t aph = 0;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = p.n_peer ? true : ((p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0));
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
       mbar_wait(&acc_full[a], aph);
@@ -232,7 +238,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float4 v = *reinterpret_cast<const float4*>(tile + rr * EPI_LD + cq);
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             if (grow < p.M) {
-              float4* dst = reinterpret_cast<float4*>(p.C + (size_t)grow * p.ldc + col0 + cq);
+              float4* dst;
+              if (p.n_peer) {                       // a 32-column chunk never straddles two ranks (kc % 32 == 0)
+                const int q = col0 / p.kc;
+                dst = reinterpret_cast<float4*>(p.Cp[q] + (size_t)(p.row_off + grow) * p.kc + (col0 - q * p.kc) + cq);
+              } else {
+                dst = reinterpret_cast<float4*>(p.C + (size_t)grow * p.ldc + col0 + cq);
+              }
               if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
               *dst = v;
             }
@@ -333,6 +345,7 @@ static int gemm_dispatch(const float* A, int64_t lda, const float* B_hi, const f
     return B200GNN_ERR_UNSUPPORTED;
   gemm::Params p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = accumulate ? 1 : 0;
+  p.n_peer = 0; p.kc = 0; p.row_off = 0;
   if (N <= 48) return gemm::launch<gemm::Cfg<48, 4>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
   return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
 }
@@ -347,4 +360,25 @@ extern "C" int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float*
 extern "C" int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
                                            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, void* stream) {
   return gemm_dispatch(A, lda, B_hi, B_lo, ldb, C, ldc, M, N, K, nullptr, 1, stream);
+}
+
+// C = A · B^T (+bias) with the output SCATTERED BY COLUMN BLOCK to `world` destination buffers: columns [q*kc, (q+1)*kc)
+// -> C_ptrs[q][(row_off + m) * kc + ...] (each an [*, kc] row-major matrix; for the multi-GPU engine these are the ranks'
+// C-layout buffers, peer-mapped).  kc = N / world must be a multiple of 32.  C_ptrs: HOST array of `world` device pointers.
+extern "C" int b200gnn_gemm_tf32x3_scatter_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                               float* const* C_ptrs, int32_t world, int64_t row_off, int64_t M, int64_t N, int64_t K,
+                                               const float* bias, void* stream) {
+  if (!A || !B_hi || !B_lo || !C_ptrs || world <= 0 || world > 16 || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || row_off < 0 ||
+      M >= INT32_MAX || N >= INT32_MAX || K >= INT32_MAX)
+    return B200GNN_ERR_BAD_ARG;
+  if (N % world || (N / world) % 32 || N <= 48) return B200GNN_ERR_UNSUPPORTED;
+  if (lda % 4 || ldb % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16)) return B200GNN_ERR_UNSUPPORTED;
+  gemm::Params p;
+  p.C = nullptr; p.bias = bias; p.ldc = N; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = 0;
+  p.n_peer = world; p.kc = (int32_t)(N / world); p.row_off = row_off;
+  for (int q = 0; q < world; ++q) {
+    if (!C_ptrs[q] || !aligned_to(C_ptrs[q], 16)) return B200GNN_ERR_BAD_ARG;
+    p.Cp[q] = C_ptrs[q];
+  }
+  return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
 }

@@ -46,7 +46,23 @@ struct SpmmParams {
   int32_t hub_threshold, seg_len, n_hub, n_seg, n_chunks;
   int32_t mean, stream_store, main_grid;
   int32_t n_slabs, l2_hint;   // bulk kernel: column slabs (slab-major grid), evict_last policy on the gathers
+  // Fused C->R layout exchange of the multi-GPU engine (hybrid.py): output row i of this [n_rows, K] product belongs to the
+  // rank q with yoff[q] <= i < yoff[q+1] and is stored to Yp[q] + (i - yoff[q]) * ldyp + ycol (float index): the aggregation's
+  // epilogue writes straight into the consumers' R-layout buffers (peer mappings).  n_yp = 0: off (plain Y / ldy).
+  float* Yp[16];
+  int32_t yoff[17];
+  int32_t n_yp, ycol;
+  int64_t ldyp;
 };
+
+// address of output row `row` (float4 units) for the kernels that support the fused C->R scatter
+__device__ __forceinline__ float4* y_row_v4(const SpmmParams& p, int row) {
+  if (p.n_yp == 0) return reinterpret_cast<float4*>(p.Y) + (size_t)row * (size_t)(p.ldy / 4);
+  int q = 0;
+#pragma unroll 1
+  while (q + 1 < p.n_yp && row >= p.yoff[q + 1]) ++q;
+  return reinterpret_cast<float4*>(p.Yp[q] + (size_t)(row - p.yoff[q]) * (size_t)p.ldyp + p.ycol);
+}
 
 struct LaneMap {
   int lpr, groups, g, l;
@@ -559,7 +575,7 @@ __device__ __forceinline__ void spmm_chunk_cta_bulk(const SpmmParams& p, const i
       float4 y = acc[j];
       if (p.mean) vdiv(y, (float)max(deg, 1));
       vadd(y, bias4[j]);
-      float4* dst = Yv + (size_t)row * ldyv + lane + 32 * j;
+      float4* dst = (p.n_yp ? y_row_v4(p, row) + slab_voff : Yv + (size_t)row * ldyv) + lane + 32 * j;
       if (p.stream_store) vstcs(dst, y); else *dst = y;
       if (STATS) vstat(ssum[j], ssq[j], y);
       vzero(acc[j]);
@@ -778,7 +794,7 @@ __device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const
     }
     if (p.mean) vdiv(acc, (float)max(deg, 1));
     if (p.bias) vadd(acc, bias4);
-    Yv[(size_t)row * ldyv + l] = acc;
+    if (p.n_yp) y_row_v4(p, row)[l] = acc; else Yv[(size_t)row * ldyv + l] = acc;
   }
 }
 
@@ -821,7 +837,7 @@ __global__ void __launch_bounds__(256) spmm_hub_finalize_kernel(const SpmmParams
       acc.x += __ldg(p.bias + 4 * v); acc.y += __ldg(p.bias + 4 * v + 1);
       acc.z += __ldg(p.bias + 4 * v + 2); acc.w += __ldg(p.bias + 4 * v + 3);
     }
-    *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + 4 * v) = acc;
+    if (p.n_yp) y_row_v4(p, row)[v] = acc; else *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + 4 * v) = acc;
     if (stat) {
       *reinterpret_cast<float4*>(stat + 4 * v) = acc;
       *reinterpret_cast<float4*>(stat + p.K + 4 * v) = make_float4(acc.x * acc.x, acc.y * acc.y, acc.z * acc.z, acc.w * acc.w);
@@ -1079,6 +1095,9 @@ using namespace b200gnn;
 // see the variant word in b200gnn_spmm_csr_f32
 static int g_spmm_variant = 0;
 
+struct ScatterArgs { int n; float* ptr[16]; int32_t off[17]; int64_t ld, col; };
+static thread_local ScatterArgs g_scatter = {0, {}, {}, 0, 0};
+
 // Slab width (floats) the bulk kernel uses when left to choose.  Measured on B200 (ARXIV-shape, profiles/r2_spmm_sweep):
 // the copy engine retires ~20 G row copies/s chip-wide whatever their size (tools/bulk_probe.cu), so narrower slabs
 // lose more to the per-copy cost than their L2 residency wins back (K=256: one 1 KB copy per neighbour 0.263 ms,
@@ -1159,6 +1178,15 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   else if (K % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0 && aligned_to(X, 8) && aligned_to(Y, 8)) W = 2;
   p.nvec = (int32_t)(K / W);
   p.n_slabs = 1; p.l2_hint = 0;
+  p.n_yp = 0; p.ycol = 0; p.ldyp = 0;
+  if (g_scatter.n > 0) {            // set by b200gnn_spmm_csr_scatter_f32 around this call (same thread)
+    if (W != 4 || K % 4 || g_scatter.ld % 4 || g_scatter.col % 4) return B200GNN_ERR_UNSUPPORTED;
+    const bool ok_kernel = (K % 128 == 0 && K <= 4096) || (p.nvec <= 16 && !stat_partial);
+    if (!ok_kernel || (g_spmm_variant & 15) == 1 || (g_spmm_variant & 15) == 2) return B200GNN_ERR_UNSUPPORTED;
+    p.n_yp = g_scatter.n; p.ycol = (int32_t)g_scatter.col; p.ldyp = g_scatter.ld;
+    for (int q = 0; q < g_scatter.n; ++q) { p.Yp[q] = g_scatter.ptr[q]; p.yoff[q] = g_scatter.off[q]; }
+    p.yoff[g_scatter.n] = g_scatter.off[g_scatter.n];
+  }
 
   // Variant word (b200gnn_spmm_set_variant; tuning and A/B tests): low nibble = kernel family
   //   0 automatic, 1 register-staged, 2 cp.async ring (round-1 kernel), 3 bulk-copy ring, one slab of min(K,256) floats
@@ -1223,4 +1251,30 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
     if ((rc = check_launch())) return rc;
   }
   return B200GNN_OK;
+}
+
+// The same product with the C->R layout exchange of the multi-GPU engine fused into the epilogue: output row i goes to
+// Y_ptrs[q][(i - row_off[q]) * ldy_dst + col_dst ...] for the rank q that owns it (row_off: world+1 ascending offsets, HOST
+// array; Y_ptrs: HOST array of `world` device pointers, peer-mapped R-layout buffers).  Supported where the TMA kernels
+// (K % 128 == 0) or the narrow kernel (K <= 64, no statistics) run; Y itself is not written.
+extern "C" int b200gnn_spmm_csr_scatter_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                                            int64_t ldx, float* const* Y_ptrs, const int32_t* row_off, int32_t world,
+                                            int64_t ldy_dst, int64_t col_dst, int64_t n_rows, int64_t n_src, int64_t K, int reduce,
+                                            const float* bias, const int32_t* chunk_rowptr, int64_t n_chunks,
+                                            int32_t hub_threshold, int32_t seg_len, const int32_t* hub_rows,
+                                            const int32_t* hub_segptr, int64_t n_hub, int64_t n_seg, float* hub_workspace,
+                                            void* stream) {
+  if (!Y_ptrs || !row_off || world <= 0 || world > 16 || ldy_dst < K || col_dst < 0 || row_off[0] != 0 || row_off[world] != n_rows)
+    return B200GNN_ERR_BAD_ARG;
+  g_scatter.n = world; g_scatter.ld = ldy_dst; g_scatter.col = col_dst;
+  for (int q = 0; q < world; ++q) {
+    if (!Y_ptrs[q] || !aligned_to(Y_ptrs[q], 16) || row_off[q + 1] < row_off[q]) { g_scatter.n = 0; return B200GNN_ERR_BAD_ARG; }
+    g_scatter.ptr[q] = Y_ptrs[q]; g_scatter.off[q] = row_off[q];
+  }
+  g_scatter.off[world] = row_off[world];
+  // Y: any aligned non-null pointer passes the checks of the plain entry point; it is never dereferenced in scatter mode
+  const int rc = b200gnn_spmm_csr_f32(rowptr, col, val, X, ldx, Y_ptrs[0], K, n_rows, n_src, K, reduce, bias, nullptr, chunk_rowptr,
+                                      n_chunks, hub_threshold, seg_len, hub_rows, hub_segptr, n_hub, n_seg, hub_workspace, stream);
+  g_scatter.n = 0;
+  return rc;
 }

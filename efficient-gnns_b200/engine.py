@@ -245,8 +245,9 @@ class GCNStudentTrainer:
                 inp = self.A[l]
         return self.Y[-1]
 
-    def backward(self, x: torch.Tensor):
-        """Consumes self.dY[-1] (d loss / d logits); fills self.grads."""
+    def backward(self, x: torch.Tensor, d_out_feat: Optional[torch.Tensor] = None):
+        """Consumes self.dY[-1] (d loss / d logits) and, for the auxiliary distillation losses, d loss / d out_feat
+        ([N, H], added to the gradient arriving at the last hidden activation); fills self.grads."""
         for l in range(self.L - 1, -1, -1):
             inp = x if l == 0 else self.A[l - 1]
             if l == self.L - 1:
@@ -255,13 +256,19 @@ class GCNStudentTrainer:
                 self._wgrad_async(0, self.AX, self.dY[0])              # dW0 = (ÂX)ᵀ dY0, no backward aggregation
                 continue
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
+            d_prev = self.dA[l - 1] if l > 0 else None
             if l > 0:
-                self._linear_dgrad(l, self.dH[l], self.dA[l - 1])
+                if d_out_feat is not None and l == self.L - 1:
+                    # the auxiliary loss's gradient w.r.t. out_feat is the starting value the input-gradient GEMM adds to
+                    d_prev = d_out_feat
+                    self._linear_dgrad(l, self.dH[l], d_prev, accumulate=True)
+                else:
+                    self._linear_dgrad(l, self.dH[l], d_prev)
             self._wgrad_async(l, inp, self.dH[l])                      # forks after the dgrad GEMM (both want the whole SM)
             if l > 0:
                 k = self.dims[l]
                 part = self._part(k)
-                ops.bn_act_bwd(self.dA[l - 1], self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
+                ops.bn_act_bwd(d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
                                self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
                                d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
         self._wgrad_join()
@@ -290,11 +297,13 @@ class GCNStudentTrainer:
         else:
             torch.mm(inp, self.W[l], out=out)
 
-    def _linear_dgrad(self, l: int, d_out: torch.Tensor, d_inp: torch.Tensor):
-        """d_inp = d_out @ W_l^T."""
+    def _linear_dgrad(self, l: int, d_out: torch.Tensor, d_inp: torch.Tensor, accumulate: bool = False):
+        """d_inp (+)= d_out @ W_l^T."""
         if self.tc_gemm:
             hi, lo = ops.split_tf32(self.W[l], transpose=False, hi=self.W_split[l][0], lo=self.W_split[l][1])
-            ops.gemm_tf32x3(d_out, hi, lo, out=d_inp)
+            ops.gemm_tf32x3(d_out, hi, lo, out=d_inp, accumulate=accumulate)
+        elif accumulate:
+            d_inp.addmm_(d_out, self.W[l].t())
         else:
             torch.mm(d_out, self.W[l].t(), out=d_inp)
 
@@ -325,10 +334,29 @@ class GCNStudentTrainer:
         self.backward(x)
         ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr)
 
-    def train_step(self, x, y, train_idx, teacher_logits=None) -> torch.Tensor:
-        """One reference ``train()`` call (kd if teacher_logits is given, else supervised).
-        Returns the device tensor [loss, loss_cls, loss_kd] (no host sync)."""
-        self._step_impl(x, y, train_idx, teacher_logits)
+    def train_step(self, x, y, train_idx, teacher_logits=None, aux=None, beta: float = 1.0) -> torch.Tensor:
+        """One reference ``train()`` call: kd if teacher_logits is given, else supervised (arxiv_pyg/gnn.py:102-195), and
+        with ``aux`` the kd + beta*aux form of gnn_kd_and_aux.py:100-189 — ``aux(out_feat)`` receives the [N, H] output
+        of the last hidden layer (the reference's ``model.out_feat``, requires_grad) and returns the auxiliary loss, e.g.
+        ``lambda f: criterion.lpw_criterion(z, y, f[idx], t_feat[idx], edge_index, "cosine", 1)[2]`` or a projection head +
+        ``nce_criterion``; parameters of such heads get their gradients through torch autograd and stay with the caller's
+        optimizer.  Returns the device tensor [loss, loss_cls, loss_kd] (+ beta*aux folded into loss); no host sync."""
+        if aux is None:
+            self._step_impl(x, y, train_idx, teacher_logits)
+            return self.loss_out
+        logits = self.forward(x, training=True)
+        self.dY[-1].zero_()
+        ops.kd_loss_fwd_bwd(logits, y, train_idx, teacher_logits, self.alpha, self.kd_T, d_logits=self.dY[-1],
+                            loss_out=self.loss_out, partial=self.kd_part)
+        feat = self.out_feat().detach().requires_grad_(True)
+        with torch.enable_grad():
+            loss_aux = aux(feat)
+            (loss_aux * beta).backward()
+        d_feat = feat.grad if feat.grad is not None else torch.zeros_like(feat)
+        self.backward(x, d_out_feat=d_feat.contiguous())
+        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr)
+        self.loss_aux = loss_aux.detach()
+        self.loss_out[0].add_(self.loss_aux * beta)
         return self.loss_out
 
     # ------------------------------------------------------------------ CUDA graph

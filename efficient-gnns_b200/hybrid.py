@@ -154,6 +154,19 @@ class PeerExchange:
     def buffer(self, name: str, shape, device) -> torch.Tensor:
         return self.arena.alloc(name, shape)
 
+    def fused_r2c_targets(self, name: str):
+        """Raw addresses of every rank's C-layout buffer `name` (rank order = column-block order): the GEMM epilogue stores
+        its tiles there directly (b200gnn_gemm_tf32x3_scatter_f32); follow with barrier()."""
+        return [self.arena.peer_ptr(name, q, 0) for q in range(self.world)]
+
+    def barrier(self):
+        self.arena.barrier()
+
+    def fused_c2r_targets(self, name: str):
+        """Raw addresses of every rank's R-layout buffer `name` ([block, K]); producers store row i of their C-layout result at
+        (i - offsets[q], rank*kc ...) of rank q's buffer; follow with barrier()."""
+        return [self.arena.peer_ptr(name, q, 0) for q in range(self.world)]
+
     def r2c(self, src: torch.Tensor, dst: torch.Tensor, name: str):
         from .peer import copy2d
         P, n_p, K = self.world, self.n_p, src.shape[1]
@@ -200,8 +213,10 @@ def _numel(shape) -> int:
 class HybridGCNTrainer(GCNStudentTrainer):
     """One rank of the hybrid-layout GCN student; same step semantics as GCNStudentTrainer (engine.py)."""
 
-    def __init__(self, adj: SparseTensor, dims: List[int], group=None, exchange: str = "peer", _fake=None, **kw):
+    def __init__(self, adj: SparseTensor, dims: List[int], group=None, exchange: str = "peer", _fake=None, fuse_r2c: bool = True,
+                 fuse_c2r: bool = True, **kw):
         self.group = group
+        self.fuse_r2c, self.fuse_c2r = bool(fuse_r2c), bool(fuse_c2r)
         if _fake is not None:                       # (rank, world) of a pretended run: exchange="null" only
             assert exchange == "null"
             self.rank, self.world = _fake
@@ -342,8 +357,14 @@ class HybridGCNTrainer(GCNStudentTrainer):
             k = dims[l + 1]
             if l == 0 and self.agg_first:
                 if self.col_mode[dims[0]]:
-                    ops.spmm_csr(self.Gfull, x_in, "sum", out=c["AXc"])
-                    self.ex.c2r(c["AXc"], c["AX_R"], "AX_R")
+                    kc0 = dims[0] // P
+                    if self._fusable_c2r(kc0):       # aggregation epilogue = the C->R exchange
+                        ops.spmm_csr_scatter(self.Gfull, x_in, self.ex.fused_c2r_targets("AX_R"), self.plan.offsets, dims[0],
+                                             self.rank * kc0)
+                        self.ex.barrier()
+                    else:
+                        ops.spmm_csr(self.Gfull, x_in, "sum", out=c["AXc"])
+                        self.ex.c2r(c["AXc"], c["AX_R"], "AX_R")
                     ax = c["AX_R"]
                 else:
                     ax = ops.spmm_csr(self.G, x_in, "sum", out=self.AX)
@@ -361,10 +382,14 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 continue
             src = x_in if l == 0 else inp
             self._layer_in[l] = src
-            self._linear(l, src, self.H[l])
+            if self.col_mode[k] and self._fusable(k):
+                self._linear_r2c(l, src, f"Hc{l}")           # GEMM epilogue = the R->C exchange
+            else:
+                self._linear(l, src, self.H[l])
             if self.col_mode[k]:
                 kc = k // P
-                self.ex.r2c(self.H[l], c[f"Hc{l}"], f"Hc{l}")
+                if not self._fusable(k):
+                    self.ex.r2c(self.H[l], c[f"Hc{l}"], f"Hc{l}")
                 bias_c = self._cols(self.b[l], k)
                 if last:
                     ops.spmm_csr(self.Gfull, c[f"Hc{l}"], "sum", bias=bias_c, out=c[f"Yc{l}"])
@@ -380,6 +405,13 @@ class HybridGCNTrainer(GCNStudentTrainer):
                     ops.bn_finalize(part, self.n_global, self._cols(self.gamma[l], k), self._cols(self.beta[l], k), self.bn_eps,
                                     self.bn_momentum, self._cols(self.running_mean[l], k), self._cols(self.running_var[l], k),
                                     out=self.bn_c[l])
+                    if isinstance(self.ex, PeerExchange) and self.fuse_c2r:     # activation pass = the C->R exchange of A_l
+                        ops.affine_relu_dropout_scatter(c[f"Yc{l}"], self.bn_c[l][2], self.bn_c[l][3], True, self.p, self.seed, l,
+                                                        c[f"Ac{l}"], self.step_count, self.L, self.rowmap_full, k, self.rank * kc,
+                                                        self.ex.fused_c2r_targets(f"A_R{l}"), self.plan.offsets, k)
+                        self.ex.barrier()
+                        inp = c[f"A_R{l}"]
+                        continue
                     ops.affine_relu_dropout_mapped(c[f"Yc{l}"], self.bn_c[l][2], self.bn_c[l][3], True, self.p, self.seed, l,
                                                    out=c[f"Ac{l}"], step_dev=self.step_count, step_mul=self.L,
                                                    rowmap=self.rowmap_full, k_global=k, col_offset=self.rank * kc)
@@ -408,6 +440,26 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 inp = self.A[l]
         raise AssertionError("unreachable")
 
+    def _fusable_c2r(self, kc: int, stats: bool = False) -> bool:
+        """C->R exchange performed by the producing kernel: TMA SpMM kernels (kc % 128 == 0) or the narrow kernel (kc <= 64)."""
+        return isinstance(self.ex, PeerExchange) and self.fuse_c2r and (kc % 128 == 0 or (kc <= 64 and not stats))
+
+    def _fusable(self, k: int) -> bool:
+        """R->C exchange performed by the producing GEMM's epilogue: peer exchange, tensor-core GEMM, 32-column chunks."""
+        return isinstance(self.ex, PeerExchange) and self.tc_gemm and self.fuse_r2c and (k // self.world) % 32 == 0 and k > 48
+
+    def _linear_r2c(self, l: int, inp: torch.Tensor, name: str):
+        """H = inp @ W_l stored straight into every rank's C-layout buffer `name` (no H_R, no exchange kernel)."""
+        hi, lo = ops.split_tf32(self.W[l], transpose=True, hi=self.Wt_split[l][0], lo=self.Wt_split[l][1])
+        ops.gemm_tf32x3_scatter(inp, hi, lo, self.ex.fused_r2c_targets(name), self.row0)
+        self.ex.barrier()
+
+    def _dgrad_r2c(self, l: int, d_out: torch.Tensor, name: str):
+        """dA = d_out @ W_l^T stored straight into every rank's C-layout buffer `name`."""
+        hi, lo = ops.split_tf32(self.W[l], transpose=False, hi=self.W_split[l][0], lo=self.W_split[l][1])
+        ops.gemm_tf32x3_scatter(d_out, hi, lo, self.ex.fused_r2c_targets(name), self.row0)
+        self.ex.barrier()
+
     def _eval_act(self, l: int, y: torch.Tensor, out: torch.Tensor):
         scale = self.gamma[l] * torch.rsqrt(self.running_var[l] + self.bn_eps)
         shift = self.beta[l] - self.running_mean[l] * scale
@@ -425,6 +477,7 @@ class HybridGCNTrainer(GCNStudentTrainer):
         c, P, dims, L = self.c, self.world, self.dims, self.L
         self.grads.zero_()                              # slices a rank does not own stay zero (summed over ranks later)
         d_act = None                                    # d loss / d A_{l-1} in R layout, produced by layer l's dgrad
+        fused_prev = False                              # ... or already delivered in C layout by that GEMM's epilogue
         for l in range(L - 1, -1, -1):
             k = dims[l + 1]
             last = l == L - 1
@@ -448,14 +501,20 @@ class HybridGCNTrainer(GCNStudentTrainer):
                     ops.col_sum(self.dY[l], out=self.gb[l], partial=self._part(k))
                     self.ex.r2c(self.dY[l], c[f"dYc{l}"], f"dYc{l}")
                 else:
-                    self.ex.r2c(d_act, c[f"dAc{l}"], f"dAc{l}")
+                    if not fused_prev:
+                        self.ex.r2c(d_act, c[f"dAc{l}"], f"dAc{l}")
                     bn = self.bn_c[l]
                     pk = self._part_c(kc)
                     ops.bn_act_bwd(c[f"dAc{l}"], c[f"Ac{l}"], c[f"Yc{l}"], bn[0], bn[1], self._cols(self.gamma[l], k), self.p,
                                    d_y=c[f"dYc{l}"], d_gamma=self._cols(self.ggamma[l], k), d_beta=self._cols(self.gbeta[l], k),
                                    d_bias=self._cols(self.gb[l], k), partial=pk, coef=self._coef(kc))
-                ops.spmm_csr(self.Gfull, c[f"dYc{l}"], "sum", out=c[f"dHc{l}"])
-                self.ex.c2r(c[f"dHc{l}"], c[f"dH_R{l}"], f"dH_R{l}")
+                if self._fusable_c2r(kc):            # aggregation epilogue = the C->R exchange of d H_l
+                    ops.spmm_csr_scatter(self.Gfull, c[f"dYc{l}"], self.ex.fused_c2r_targets(f"dH_R{l}"), self.plan.offsets, k,
+                                         self.rank * kc)
+                    self.ex.barrier()
+                else:
+                    ops.spmm_csr(self.Gfull, c[f"dYc{l}"], "sum", out=c[f"dHc{l}"])
+                    self.ex.c2r(c[f"dHc{l}"], c[f"dH_R{l}"], f"dH_R{l}")
                 dH = c[f"dH_R{l}"]
             else:
                 if last:
@@ -471,9 +530,16 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 self.ex.allgather_rows(self.dY[l], c[f"dYfull{l}"], f"dYfull{l}")
                 ops.spmm_csr(self.G, c[f"dYfull{l}"], "sum", out=self.dH[l])
                 dH = self.dH[l]
+            fused_prev = False
             if l > 0:
-                self._linear_dgrad(l, dH, self.dA[l - 1])
-                d_act = self.dA[l - 1]
+                k_prev = dims[l]
+                prev_first_agg = (l - 1 == 0) and self.agg_first
+                if (not prev_first_agg) and self.col_mode[k_prev] and (l - 1 < L - 1) and self._fusable(k_prev):
+                    self._dgrad_r2c(l, dH, f"dAc{l - 1}")   # input-gradient GEMM epilogue = the R->C exchange of d A_{l-1}
+                    fused_prev, d_act = True, None
+                else:
+                    self._linear_dgrad(l, dH, self.dA[l - 1])
+                    d_act = self.dA[l - 1]
             self._wgrad_async(l, hidden_in, dH)
         self._wgrad_join()
 

@@ -53,6 +53,34 @@ def spmm_csr(g: CsrGraph, x: torch.Tensor, reduce: str = "sum", bias: Optional[t
     return out
 
 
+def _host_ptr_array(ptrs):
+    import ctypes as C
+    return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+
+
+def _host_i32_array(vals):
+    import ctypes as C
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+def spmm_csr_scatter(g: CsrGraph, x: torch.Tensor, dst_ptrs, row_off, ld_dst: int, col_dst: int, reduce: str = "sum",
+                     bias: Optional[torch.Tensor] = None) -> None:
+    """Y = A·X (+bias) with output row i stored to the R-layout buffer of the rank that owns it (raw device addresses
+    dst_ptrs[q], rows row_off[q]..row_off[q+1], pitch ld_dst floats, column offset col_dst): the aggregation's epilogue performs
+    the multi-GPU engine's C->R exchange."""
+    K = x.shape[1]
+    L = lib.load()
+    ws = g.hub_workspace(K)
+    rc = L.b200gnn_spmm_csr_scatter_f32(
+        lib.dptr(g.rowptr, torch.int32, "rowptr"), lib.dptr(g.col, torch.int32, "col"), lib.dptr(g.val, torch.float32, "val"),
+        lib.dptr(x, torch.float32, "x"), x.stride(0), _host_ptr_array(dst_ptrs), _host_i32_array(row_off), len(dst_ptrs),
+        int(ld_dst), int(col_dst), g.n_rows, g.n_cols, K, _REDUCE[reduce], lib.dptr(bias, torch.float32, "bias"),
+        g.chunk_rowptr.data_ptr(), g.n_chunks, g.hub_threshold, g.seg_len,
+        g.hub_rows.data_ptr() if g.n_hub else None, g.hub_segptr.data_ptr() if g.n_hub else None,
+        g.n_hub, g.n_seg, None if ws is None else ws.data_ptr(), lib.stream_ptr())
+    lib.check(rc, "spmm_csr_scatter_f32")
+
+
 class _SpMM(torch.autograd.Function):
     """matmul(adj, x, reduce): backward is the same kernel on the cached CSC view
     (upstream torch_sparse spmm backward)."""
@@ -159,6 +187,20 @@ def affine_relu_dropout_mapped(y: torch.Tensor, scale=None, shift=None, relu: bo
     return out
 
 
+def affine_relu_dropout_scatter(y: torch.Tensor, scale, shift, relu: bool, p: float, seed: int, offset: int, out: torch.Tensor,
+                                step_dev, step_mul: int, rowmap, k_global: int, col_offset: int, dst_ptrs, row_off,
+                                ld_dst: int) -> torch.Tensor:
+    """affine_relu_dropout_mapped that ALSO stores every output row into the R-layout buffer of the rank owning the node
+    (the multi-GPU engine's C->R exchange fused into the activation pass)."""
+    n, K = y.shape
+    lib.check(lib.load().b200gnn_affine_relu_dropout_scatter_f32(
+        _f32(y, "y"), _f32(out, "out"), n, K, _f32(scale, "scale"), _f32(shift, "shift"), int(relu), p, seed, offset,
+        lib.dptr(step_dev, torch.int32, "step_dev"), step_mul, lib.dptr(rowmap, torch.int32, "rowmap"), 0, k_global, col_offset,
+        _host_ptr_array(dst_ptrs), _host_i32_array(row_off), len(dst_ptrs), int(ld_dst), lib.stream_ptr()),
+        "affine_relu_dropout_scatter_f32")
+    return out
+
+
 def dropout_mask(n_rows: int, K: int, p: float, seed: int, offset: int, device="cuda") -> torch.Tensor:
     """The keep-mask (uint8 [n,K]) that affine_relu_dropout uses for (seed, offset)."""
     mask = torch.empty(n_rows, K, dtype=torch.uint8, device=device)
@@ -248,6 +290,20 @@ def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: O
                                         b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K,
                                         _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_f32")
     return out
+
+
+def gemm_tf32x3_scatter(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, dst_ptrs, row_off: int,
+                        bias: Optional[torch.Tensor] = None) -> None:
+    """a[M,K] @ b[N,K]^T with column block q of the result stored to the [*, N/world] matrix at raw device address
+    dst_ptrs[q] (rows row_off + m): the GEMM epilogue performs the multi-GPU engine's R->C exchange (peer-mapped targets)."""
+    import ctypes as C
+    M, K = a.shape
+    N = b_hi.shape[0]
+    world = len(dst_ptrs)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in dst_ptrs])
+    lib.check(lib.load().b200gnn_gemm_tf32x3_scatter_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                         b_hi.stride(0), arr, world, int(row_off), M, N, K, _f32(bias, "bias"),
+                                                         lib.stream_ptr()), "gemm_tf32x3_scatter_f32")
 
 
 def wgrad_supported(k_in: int, n_out: int) -> bool:

@@ -114,6 +114,17 @@ int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col,
                          int32_t seg_len, const int32_t* hub_rows,
                          const int32_t* hub_segptr, int64_t n_hub,
                          int64_t n_seg, float* hub_workspace, void* stream);
+/* The same product with the C->R layout exchange of the multi-GPU engine fused into the epilogue: output row i is stored to
+ * Y_ptrs[q][(i - row_off[q]) * ldy_dst + col_dst ...] for the rank q that owns it (HOST arrays: `world` peer-mapped device
+ * pointers, world+1 ascending row offsets).  Supported where the TMA kernels (K % 128 == 0) or the narrow kernel (K <= 64,
+ * no fused statistics) run, else B200GNN_ERR_UNSUPPORTED. */
+int b200gnn_spmm_csr_scatter_f32(const int32_t* rowptr, const int32_t* col, const float* val, const float* X,
+                                 int64_t ldx, float* const* Y_ptrs, const int32_t* row_off, int32_t world,
+                                 int64_t ldy_dst, int64_t col_dst, int64_t n_rows, int64_t n_src, int64_t K,
+                                 int reduce, const float* bias, const int32_t* chunk_rowptr, int64_t n_chunks,
+                                 int32_t hub_threshold, int32_t seg_len, const int32_t* hub_rows,
+                                 const int32_t* hub_segptr, int64_t n_hub, int64_t n_seg,
+                                 float* hub_workspace, void* stream);
 
 /* ------------------------------------------------------------------ *
  * Dense row-major [n_rows,K] passes between the aggregations of a layer:
@@ -166,6 +177,14 @@ int b200gnn_affine_relu_dropout_mapped_f32(const float* Y, float* out, int64_t n
                                            uint64_t seed, uint64_t offset, const int32_t* step_dev,
                                            uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
                                            int64_t K_global, int64_t col_offset, void* stream);
+/* ... with the C->R layout exchange fused: every output row is ALSO stored to the R-layout buffer of the rank owning the node:
+ * dst_ptrs[q] + (r - row_off[q]) * ld_dst + col_offset (HOST arrays of `world` peer-mapped device pointers / world+1 offsets). */
+int b200gnn_affine_relu_dropout_scatter_f32(const float* Y, float* out, int64_t n_rows, int64_t K,
+                                            const float* scale, const float* shift, int relu, float p,
+                                            uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                                            uint64_t step_mul, const int32_t* rowmap, uint64_t row_offset,
+                                            int64_t K_global, int64_t col_offset, float* const* dst_ptrs,
+                                            const int32_t* row_off, int32_t world, int64_t ld_dst, void* stream);
 int b200gnn_dropout_mask_u8(uint8_t* mask, int64_t n_rows, int64_t K, float p,
                             uint64_t seed, uint64_t offset, void* stream);
 /* Backward of out = dropout_p(relu(BN_train(Y))): given dOut, out (for the
@@ -248,6 +267,13 @@ int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
 int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                 int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                                 void* stream);
+/* Same GEMM with the R->C layout exchange of the multi-GPU engine fused into the epilogue: output columns
+ * [q*kc, (q+1)*kc), kc = N/world (a multiple of 32), are stored to C_ptrs[q][(row_off + m)*kc + ...] — C_ptrs is a HOST array
+ * of `world` device pointers (the ranks' [N_nodes, kc] buffers, peer-mapped), so the tile results cross NVLink as they are
+ * produced and no separate exchange kernel runs (the caller follows with b200gnn_peer_barrier). */
+int b200gnn_gemm_tf32x3_scatter_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
+                                    int64_t ldb, float* const* C_ptrs, int32_t world, int64_t row_off,
+                                    int64_t M, int64_t N, int64_t K, const float* bias, void* stream);
 
 /* Weight gradient  dW[Kin,Nout] = X[Nn,Kin]^T * G[Nn,Nout]  (GCNConv weight.grad / nn.Linear weight.grad^T),
  * split-K over the node index on tcgen05 (3xTF32), partials reduced in fixed order.

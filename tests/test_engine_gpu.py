@@ -187,3 +187,78 @@ def test_config0_plumbing_shape_two_layer_gcn():
     assert rel_err(tr.Y[-1], ref_logits) < 1e-5 and rel_err(tr.A[-1], ref_hidden) < 1e-5
     assert abs(loss[0] - ref_loss[0]) < 1e-5 * abs(ref_loss[0])
     assert rel_err(tr.gW[1], ref_grads[4]) < 2e-5 and rel_err(tr.gW[0], ref_grads[0]) < 5e-5
+
+
+@pytest.mark.parametrize("aux_name", ["lpw", "nce_head", "at"])
+def test_gcn_step_with_auxiliary_distillation_loss_matches_oracle(aux_name):
+    """kd + beta*aux, the train() of arxiv_pyg/gnn_kd_and_aux.py:100-189, on the fused engine: the auxiliary criterion runs on
+    out_feat[train_idx] (LSP on the train-induced subgraph :150-160; a projection head + nce_criterion :161-171; AT :128-137),
+    its gradient w.r.t. out_feat seeds the input-gradient GEMM (accumulating epilogue) and every engine gradient must match
+    the fp64 restatement of the whole step; a torch-side head receives its gradient through autograd."""
+    from efficient_gnns_b200 import criterion as C
+    tr, rc, x, y, t, idx = build(p=0.0, dims=(32, 64, 64, 8))
+    n, H = x.shape[0], tr.dims[-2]
+    g = torch.Generator().manual_seed(3)
+    t_feat = torch.randn(n, 24, generator=g).relu() + 0.01
+    m = idx.numel()
+    sub = torch.from_numpy(og.subgraph(idx.numpy(), np.stack(rc), True)[0])          # arxiv_pyg/gnn.py:249
+    head_w = (torch.randn(16, H, generator=g) * 0.2)
+    beta = 0.7
+    yc, ic, tc, tfc = y.cuda(), idx.cuda(), t.cuda(), t_feat.cuda()
+    head = torch.nn.Parameter(head_w.clone().cuda())
+
+    def aux_gpu(f):
+        z = tr.Y[-1][ic]
+        if aux_name == "lpw":
+            return C.lpw_criterion(z, yc[ic], f[ic], tfc[ic], sub.cuda(), "cosine", 1.0)[2]
+        if aux_name == "at":
+            return C.at_criterion(z, yc[ic], f[ic], tfc[ic], 1.0)[2]
+        return C.nce_criterion(z, yc[ic], f[ic] @ head.t(), tfc[ic][:, :16], 1.0, 0.075, 10 ** 9)[2]
+
+    loss = tr.train_step(x.cuda(), yc, ic, tc, aux=aux_gpu, beta=beta).cpu()
+
+    # fp64 restatement of the same step
+    r, c, v = og.gcn_norm(rc[0], rc[1], n)
+    ptr, c, v = torch.from_numpy(og.ind2ptr(r, n)), torch.from_numpy(c), torch.from_numpy(v).double()
+    sd = {k: w.cpu().double() for k, w in tr.state_dict().items()}
+    # (state_dict is read AFTER the step: rebuild the pre-step parameters from a twin engine with the same seed)
+    tr0, *_ = build(p=0.0, dims=(32, 64, 64, 8))
+    sd = {k: w.cpu().double() for k, w in tr0.state_dict().items()}
+    L = tr.L
+    W = [sd[f"convs.{i}.weight"].clone().requires_grad_(True) for i in range(L)]
+    B = [sd[f"convs.{i}.bias"].clone().requires_grad_(True) for i in range(L)]
+    ga = [sd[f"bns.{i}.weight"].clone().requires_grad_(True) for i in range(L - 1)]
+    be = [sd[f"bns.{i}.bias"].clone().requires_grad_(True) for i in range(L - 1)]
+    hw = head_w.double().clone().requires_grad_(True)
+    logits, hidden = onn.gcn_forward(x.double(), ptr, c, v, W, B, ga, be, None, p=0.0)
+    kd, lc, la = oc.kd_criterion(logits[idx], y[idx], t[idx].double(), tr.alpha, tr.kd_T)
+    f, tf = hidden[idx], t_feat[idx].double()
+    if aux_name == "lpw":
+        aux = oc.lpw_criterion(logits[idx], y[idx], f, tf, sub, "cosine", 1.0)[2]
+    elif aux_name == "at":
+        aux = oc.at_criterion(logits[idx], y[idx], f, tf, 1.0)[2]
+    else:
+        aux = oc.nce_criterion(logits[idx], y[idx], f @ hw.t(), tf[:, :16], 1.0, 0.075, 10 ** 9)[2]
+    total = kd + beta * aux
+    params = []
+    for i in range(L):
+        params += [W[i], B[i]]
+        if i < L - 1:
+            params += [ga[i], be[i]]
+    grads = torch.autograd.grad(total, params + [hw], allow_unused=True)
+    assert abs(loss[0] - float(total)) < 2e-5 * abs(float(total))
+    assert abs(float(tr.loss_aux) - float(aux)) < 2e-5 * abs(float(aux)) + 1e-9
+    got = []
+    for l in range(L):
+        got += [tr.gW[l], tr.gb[l]]
+        if l < L - 1:
+            got += [tr.ggamma[l], tr.gbeta[l]]
+    scale = max(gr.abs().max().item() for gr in grads[:-1])
+    for i, (a, b) in enumerate(zip(got, grads[:-1])):
+        if (i % 4 == 1) and i < 4 * (L - 1):
+            assert a.abs().max().item() < 1e-5 * scale
+        else:
+            # InfoNCE at T = 0.075 multiplies the logits by 13: its own gradient test runs at 5e-5, through the network 1e-4
+            assert rel_err(a, b) < (1e-4 if aux_name == "nce_head" else 5e-5), f"grad {i}"
+    if aux_name == "nce_head":
+        assert rel_err(head.grad, grads[-1] ) < 5e-5
