@@ -42,3 +42,12 @@ def test_allgather_node_parallel_step_equals_single_gpu():
         pytest.skip("needs 2 GPUs")
     rc, out = _torchrun(2, "dist_equiv.py")
     assert rc == 0 and "DIST_EQUIV PASS" in out, out
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_head_parallel_gat_layer_equals_single_gpu(mode):
+    """BASELINE configs[3] (GAT teacher, 1->8 GPUs): the head-parallel layer of hybrid_gat.py vs nn.DGLGATConv on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rc, out = _torchrun(2, "hybrid_gat_equiv.py", mode)
+    assert rc == 0 and f"HYBRID_GAT_EQUIV {mode} P=2 PASS" in out, out
