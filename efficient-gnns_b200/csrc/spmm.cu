@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_bulk_kernel(const S
 // A 160-byte row needs only 10 lanes.  Instead of folding several NEIGHBOURS of one row across the warp (which drains
 // at every row end and needs cross-group shuffles), each group of lanes takes its OWN ROW of the chunk: 3 rows
 // (K=40) advance concurrently per warp, each with 4 independent 128-bit gathers in flight, no shuffles at all.
-template <bool HAS_VAL>
+template <bool HAS_VAL, int U>
 __device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const int cta) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lpr = p.nvec, groups = 32 / lpr;
@@ -768,24 +768,34 @@ __device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const
     if (deg > p.hub_threshold) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int e = beg;
-    if (e + 4 <= end) {                              // software-pipelined: the next batch's (col,val) load overlaps this batch's gathers
-      int c[4]; float w[4];
+    if (e + U <= end) {                              // software-pipelined: the next batch's (col,val) load overlaps this batch's gathers
+      int c[U]; float w[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + u); w[u] = HAS_VAL ? __ldg(p.val + e + u) : 1.f; }
-      for (; e + 4 <= end; e += 4) {
-        float4 x[4];
+      for (int u = 0; u < U; ++u) { c[u] = __ldg(p.col + e + u); w[u] = HAS_VAL ? __ldg(p.val + e + u) : 1.f; }
+      for (; e + U <= end; e += U) {
+        float4 x[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
-        float wc[4];
+        for (int u = 0; u < U; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
+        float wc[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) wc[u] = w[u];
-        if (e + 8 <= end) {
+        for (int u = 0; u < U; ++u) wc[u] = w[u];
+        if (e + 2 * U <= end) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + 4 + u); w[u] = HAS_VAL ? __ldg(p.val + e + 4 + u) : 1.f; }
+          for (int u = 0; u < U; ++u) { c[u] = __ldg(p.col + e + U + u); w[u] = HAS_VAL ? __ldg(p.val + e + U + u) : 1.f; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) vfma(acc, wc[u], x[u]);
+        for (int u = 0; u < U; ++u) vfma(acc, wc[u], x[u]);
       }
+    }
+    if (U > 4 && e + 4 <= end) {                     // a half batch before the scalar tail
+      int c[4]; float w[4]; float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { c[u] = __ldg(p.col + e + u); w[u] = HAS_VAL ? __ldg(p.val + e + u) : 1.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = vldg(Xv + (size_t)c[u] * ldxv + l);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vfma(acc, w[u], x[u]);
+      e += 4;
     }
     for (; e < end; ++e) {
       const int c = __ldg(p.col + e);
@@ -798,11 +808,11 @@ __device__ __forceinline__ void spmm_chunk_cta_narrow(const SpmmParams& p, const
   }
 }
 
-template <bool HAS_VAL>
+template <bool HAS_VAL, int U>
 __global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_rows_narrow_kernel(const SpmmParams p) {
   __shared__ float s_mem[SPMM_MAX_SLAB_FLOATS];
   if ((int)blockIdx.x < p.n_seg) spmm_hub_seg_cta<float4, 1, HAS_VAL>(p, (int)blockIdx.x, s_mem);
-  else spmm_chunk_cta_narrow<HAS_VAL>(p, (int)blockIdx.x - p.n_seg);
+  else spmm_chunk_cta_narrow<HAS_VAL, U>(p, (int)blockIdx.x - p.n_seg);
 }
 
 // Sum a hub row's segment partials in segment order, apply the epilogue.
@@ -1229,8 +1239,9 @@ extern "C" int b200gnn_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, c
   if (narrow_ok) {
     rc = B200GNN_OK;
     const int grid = p.main_grid + p.n_seg;
-    if (p.val) spmm_rows_narrow_kernel<true><<<grid, SPMM_THREADS, 0, st>>>(p);
-    else spmm_rows_narrow_kernel<false><<<grid, SPMM_THREADS, 0, st>>>(p);
+    const bool deep = (g_spmm_variant & 128) != 0;   // +128: 8 gathers in flight per lane group instead of 4 (A/B)
+    if (p.val) { if (deep) spmm_rows_narrow_kernel<true, 8><<<grid, SPMM_THREADS, 0, st>>>(p); else spmm_rows_narrow_kernel<true, 4><<<grid, SPMM_THREADS, 0, st>>>(p); }
+    else { if (deep) spmm_rows_narrow_kernel<false, 8><<<grid, SPMM_THREADS, 0, st>>>(p); else spmm_rows_narrow_kernel<false, 4><<<grid, SPMM_THREADS, 0, st>>>(p); }
     if ((rc = check_launch())) return rc;
     if (p.n_hub > 0) {
       spmm_hub_finalize_kernel<<<p.n_hub, 256, 0, st>>>(p);

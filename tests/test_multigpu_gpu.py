@@ -51,3 +51,12 @@ def test_head_parallel_gat_layer_equals_single_gpu(mode):
         pytest.skip("needs 2 GPUs")
     rc, out = _torchrun(2, "hybrid_gat_equiv.py", mode)
     assert rc == 0 and f"HYBRID_GAT_EQUIV {mode} P=2 PASS" in out, out
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_feature_parallel_rgcn_inference_equals_single_gpu(mode):
+    """BASELINE configs[4] (R-GCN on MAG-shape, 2/4/8 GPUs): rgcn.RGCNInference with per-type R<->C exchanges vs one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rc, out = _torchrun(2, "hybrid_rgcn_equiv.py", mode)
+    assert rc == 0 and f"HYBRID_RGCN_EQUIV {mode} P=2 PASS" in out, out

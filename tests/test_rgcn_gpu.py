@@ -116,3 +116,16 @@ def test_group_input_typed_gather_and_deterministic_scatter():
         emb[str(k)].grad = None
     (bnn.group_input(x_dict, emb, nt, li, F_) * w).sum().backward()
     assert all(torch.equal(a, emb[str(k)].grad) for a, k in zip(g1, (1, 2)))
+
+
+def test_full_batch_rgcn_engine_matches_reference_inference_fixture(golden_rgcn):
+    """efficient_gnns_b200.rgcn.RGCNInference (relation CSRs built once by the ingestion kernels, aggregate-then-transform with
+    the accumulating tcgen05 epilogue) vs the output of the reference's own RGCN.inference (mag_pyg/gnn.py:140-171)."""
+    from efficient_gnns_b200.rgcn import RGCNInference
+    G = golden_rgcn
+    eng = RGCNInference(G["state"], G["num_nodes"], G["edge_index_dict"], G["key2int"])
+    out = eng({0: G["x_paper"]})
+    for t in range(3):
+        assert rel_err(out[t], G["out_inference"][t]) < 1e-5
+    out2 = eng({0: G["x_paper"]})                      # buffers are reused: a second call gives identical bits
+    assert all(torch.equal(out[t], out2[t]) for t in range(3))

@@ -232,3 +232,24 @@ def test_spmm_bulk_tiny_and_ragged(variant, spmm_variant):
         ref = oo.spmm_scatter(row, col, val.double(), x.double(), n_rows, "sum")
         out = make_adj(row, col, n_rows, n_cols, val).matmul(x.cuda(), "sum")
         assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("K", [8, 16, 32, 40, 64])
+def test_spmm_narrow_deep_pipeline_variant(K, spmm_variant):
+    """variant +128: the multi-row-per-warp narrow kernel with 8 instead of 4 gathers in flight per lane group (the widths the
+    multi-GPU engine's column slices and the 40 logits use): identical results, hub rows and ragged tails included."""
+    n = 20_000
+    g = torch.Generator().manual_seed(K)
+    row = torch.cat([torch.full((9000,), 5), torch.randint(0, n, (120_000,), generator=g)])
+    col = torch.cat([torch.randperm(n, generator=g)[:9000], torch.randint(0, n, (120_000,), generator=g)])
+    r, c, _ = og.coalesce(row.numpy(), col.numpy(), n)
+    r, c = torch.from_numpy(r), torch.from_numpy(c)
+    val = torch.rand(r.numel(), generator=g)
+    x = torch.randn(n, K, generator=g)
+    G = make_adj(r, c, n, n, val).storage.engine_csr()
+    ref = oo.spmm_scatter(r, c, val.double(), x.double(), n, "sum")
+    spmm_variant(0)
+    a = ops.spmm_csr(G, x.cuda(), "sum")
+    spmm_variant(128)
+    b = ops.spmm_csr(G, x.cuda(), "sum")
+    assert rel_err(a, ref) < TOL and rel_err(b, ref) < TOL
