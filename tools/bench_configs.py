@@ -70,6 +70,37 @@ def main():
         print(json.dumps(dict(config=3, what="3-layer SAGE + G-CRD full step (module path, autograd, torch Adam/BN)", S=S,
                               nnz_sym=nnz, ms_per_step=ms, edges_per_s=6 * nnz / ms * 1e3)), flush=True)
 
+    # ---- config 3 on the fused engine (engine_sage.SAGEStudentTrainer): no autograd tape, no torch BN/Adam on the student
+    if only in (None, 3):
+        from efficient_gnns_b200.engine_sage import SAGEStudentTrainer
+        tl = ds.teacher_logits.to(dev)
+        for S in (8192, 16384):
+            torch.manual_seed(0)
+            tr = SAGEStudentTrainer(adj, [128, 256, 256, 40], dropout=0.5, lr=0.01, seed=0)
+            sproj = torch.nn.Sequential(bnn.Linear(256, 256), torch.nn.BatchNorm1d(256), torch.nn.ReLU()).to(dev)
+            tproj = torch.nn.Sequential(bnn.Linear(752, 256), torch.nn.BatchNorm1d(256), torch.nn.ReLU()).to(dev)
+            tf = F.pad(t_feat, (0, 2))
+            opt = torch.optim.Adam(list(sproj.parameters()) + list(tproj.parameters()), lr=0.01)
+
+            def aux(f):
+                return C.nce_criterion(tr.Y[-1][idx], y[idx], sproj(f[idx]), tproj(tf[idx]), 1.0, 0.075, S)[2]
+
+            def step():
+                opt.zero_grad()
+                tr.train_step(x, y, idx, tl, aux=aux, beta=0.1)
+                opt.step()
+            ms = med_time(step, 8, 3)
+            print(json.dumps(dict(config=3, what="3-layer SAGE + kd + G-CRD full step on the FUSED engine (student: b200gnn kernels only; "
+                                                 "projection heads + their Adam on the module path), chunked InfoNCE without the SxS logits", S=S,
+                                  nnz_sym=nnz, ms_per_step=ms, edges_per_s=6 * nnz / ms * 1e3)), flush=True)
+        tr = SAGEStudentTrainer(adj, [128, 256, 256, 40], dropout=0.5, lr=0.01, seed=0)
+        tr.capture(x, y, idx, tl, warmup=2)
+        ms = med_time(lambda: tr.replay(), 20, 5)
+        print(json.dumps(dict(config=3, what="3-layer SAGE + logit-KD, fused engine, CUDA graph (the configs[1] step with SAGEConv)",
+                              nnz_sym=nnz, ms_per_step=ms, edges_per_s=6 * nnz / ms * 1e3)), flush=True)
+        del tr
+        torch.cuda.empty_cache()
+
     # ---- config 4: GAT layer + LSP
     adj_sl = bnn._fill_diag_pattern(adj)
     if only not in (None, 4, 5):
