@@ -86,6 +86,7 @@ struct Params {
   float* Cp[16];
   int32_t n_peer, kc;
   int64_t row_off;
+  int32_t bcast;        // 1: every Cp[q] receives ALL columns at rows row_off + m (fused all-gather of a narrow result)
 };
 
 template <class C>
@@ -237,7 +238,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int grow = m0 + q * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(tile + rr * EPI_LD + cq);
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (grow < p.M) {
+            if (grow < p.M && p.n_peer && p.bcast) {
+              for (int q = 0; q < p.n_peer; ++q)
+                *reinterpret_cast<float4*>(p.Cp[q] + (size_t)(p.row_off + grow) * p.ldc + col0 + cq) = v;
+            } else if (grow < p.M) {
               float4* dst;
               if (p.n_peer) {                       // a 32-column chunk never straddles two ranks (kc % 32 == 0)
                 const int q = col0 / p.kc;
@@ -250,6 +254,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           __syncwarp();
+        } else if (row < p.M && col0 < p.N && p.n_peer && p.bcast) {
+          for (int q = 0; q < p.n_peer; ++q) {
+            float* dst = p.Cp[q] + (size_t)(p.row_off + row) * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+          }
         } else if (row < p.M && col0 < p.N) {
           float* dst = p.C + (size_t)row * p.ldc + col0;
 #pragma unroll
@@ -345,7 +356,7 @@ static int gemm_dispatch(const float* A, int64_t lda, const float* B_hi, const f
     return B200GNN_ERR_UNSUPPORTED;
   gemm::Params p;
   p.C = C; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = accumulate ? 1 : 0;
-  p.n_peer = 0; p.kc = 0; p.row_off = 0;
+  p.n_peer = 0; p.kc = 0; p.row_off = 0; p.bcast = 0;
   if (N <= 48) return gemm::launch<gemm::Cfg<48, 4>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
   return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
 }
@@ -375,10 +386,30 @@ extern "C" int b200gnn_gemm_tf32x3_scatter_f32(const float* A, int64_t lda, cons
   if (lda % 4 || ldb % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16)) return B200GNN_ERR_UNSUPPORTED;
   gemm::Params p;
   p.C = nullptr; p.bias = bias; p.ldc = N; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = 0;
-  p.n_peer = world; p.kc = (int32_t)(N / world); p.row_off = row_off;
+  p.n_peer = world; p.kc = (int32_t)(N / world); p.row_off = row_off; p.bcast = 0;
   for (int q = 0; q < world; ++q) {
     if (!C_ptrs[q] || !aligned_to(C_ptrs[q], 16)) return B200GNN_ERR_BAD_ARG;
     p.Cp[q] = C_ptrs[q];
   }
+  return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
+}
+
+// C = A · B^T (+bias) stored to EVERY destination buffer C_ptrs[q] (row pitch ldc floats) at rows row_off + m: the row
+// all-gather of a narrow result (the multi-GPU engine's [N, 40] logits operand) fused into the GEMM epilogue.
+extern "C" int b200gnn_gemm_tf32x3_bcast_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                             float* const* C_ptrs, int32_t world, int64_t row_off, int64_t ldc, int64_t M, int64_t N,
+                                             int64_t K, const float* bias, void* stream) {
+  if (!A || !B_hi || !B_lo || !C_ptrs || world <= 0 || world > 16 || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N ||
+      row_off < 0 || M >= INT32_MAX || N >= INT32_MAX || K >= INT32_MAX)
+    return B200GNN_ERR_BAD_ARG;
+  if (lda % 4 || ldb % 4 || ldc % 4 || !aligned_to(A, 16) || !aligned_to(B_hi, 16) || !aligned_to(B_lo, 16)) return B200GNN_ERR_UNSUPPORTED;
+  gemm::Params p;
+  p.C = C_ptrs[0]; p.bias = bias; p.ldc = ldc; p.M = (int32_t)M; p.N = (int32_t)N; p.K = (int32_t)K; p.accumulate = 0;
+  p.n_peer = world; p.kc = (int32_t)N; p.row_off = row_off; p.bcast = 1;
+  for (int q = 0; q < world; ++q) {
+    if (!C_ptrs[q] || !aligned_to(C_ptrs[q], 16)) return B200GNN_ERR_BAD_ARG;
+    p.Cp[q] = C_ptrs[q];
+  }
+  if (N <= 48) return gemm::launch<gemm::Cfg<48, 4>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
   return gemm::launch<gemm::Cfg<128, 3>>(A, lda, B_hi, B_lo, ldb, p, (cudaStream_t)stream);
 }

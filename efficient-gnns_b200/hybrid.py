@@ -382,8 +382,13 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 continue
             src = x_in if l == 0 else inp
             self._layer_in[l] = src
+            fused_gather = (not self.col_mode[k]) and isinstance(self.ex, PeerExchange) and self.tc_gemm and self.fuse_r2c and k % 4 == 0
             if self.col_mode[k] and self._fusable(k):
                 self._linear_r2c(l, src, f"Hc{l}")           # GEMM epilogue = the R->C exchange
+            elif fused_gather:                              # GEMM epilogue = the row all-gather of the narrow operand
+                hi, lo = ops.split_tf32(self.W[l], transpose=True, hi=self.Wt_split[l][0], lo=self.Wt_split[l][1])
+                ops.gemm_tf32x3_bcast(src, hi, lo, self.ex.fused_c2r_targets(f"Hfull{l}"), self.row0, k)
+                self.ex.barrier()
             else:
                 self._linear(l, src, self.H[l])
             if self.col_mode[k]:
@@ -423,7 +428,8 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 self.ex.c2r(c[f"Ac{l}"], c[f"A_R{l}"], f"A_R{l}")
                 inp = c[f"A_R{l}"]
             else:
-                self.ex.allgather_rows(self.H[l], c[f"Hfull{l}"], f"Hfull{l}")
+                if not fused_gather:
+                    self.ex.allgather_rows(self.H[l], c[f"Hfull{l}"], f"Hfull{l}")
                 if last:
                     ops.spmm_csr(self.G, c[f"Hfull{l}"], "sum", bias=self.b[l], out=self.Y[l])
                     return self.Y[l]

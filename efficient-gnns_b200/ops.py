@@ -306,6 +306,17 @@ def gemm_tf32x3_scatter(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor,
                                                          lib.stream_ptr()), "gemm_tf32x3_scatter_f32")
 
 
+def gemm_tf32x3_bcast(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, dst_ptrs, row_off: int, ldc: int,
+                      bias: Optional[torch.Tensor] = None) -> None:
+    """a[M,K] @ b[N,K]^T stored to EVERY buffer at raw address dst_ptrs[q] (rows row_off + m, pitch ldc): the multi-GPU
+    engine's row all-gather of a narrow result fused into the GEMM epilogue."""
+    M, K = a.shape
+    N = b_hi.shape[0]
+    lib.check(lib.load().b200gnn_gemm_tf32x3_bcast_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                       b_hi.stride(0), _host_ptr_array(dst_ptrs), len(dst_ptrs), int(row_off), int(ldc),
+                                                       M, N, K, _f32(bias, "bias"), lib.stream_ptr()), "gemm_tf32x3_bcast_f32")
+
+
 def wgrad_supported(k_in: int, n_out: int) -> bool:
     return k_in in (128, 256) and n_out % 4 == 0 and 0 < n_out <= 256
 

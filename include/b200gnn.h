@@ -274,6 +274,11 @@ int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, 
 int b200gnn_gemm_tf32x3_scatter_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                     int64_t ldb, float* const* C_ptrs, int32_t world, int64_t row_off,
                                     int64_t M, int64_t N, int64_t K, const float* bias, void* stream);
+/* ... and the row all-gather of a narrow result fused the same way: the whole [M, N] tile block is stored to EVERY
+ * C_ptrs[q] (row pitch ldc) at rows row_off + m. */
+int b200gnn_gemm_tf32x3_bcast_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
+                                  int64_t ldb, float* const* C_ptrs, int32_t world, int64_t row_off, int64_t ldc,
+                                  int64_t M, int64_t N, int64_t K, const float* bias, void* stream);
 
 /* Weight gradient  dW[Kin,Nout] = X[Nn,Kin]^T * G[Nn,Nout]  (GCNConv weight.grad / nn.Linear weight.grad^T),
  * split-K over the node index on tcgen05 (3xTF32), partials reduced in fixed order.

@@ -85,3 +85,19 @@ def test_activation_pass_c2r_scatter():
     for q in range(world):
         rows = off[q + 1] - off[q]
         assert torch.equal(dst[q][:rows, rank * kc:(rank + 1) * kc], ref[off[q]:off[q + 1]])
+
+
+@pytest.mark.parametrize("N,K", [(40, 256), (160, 64)])
+def test_gemm_epilogue_row_allgather_broadcast(N, K):
+    """b200gnn_gemm_tf32x3_bcast_f32: the [M, N] result lands in every destination buffer at rows row_off + m (narrow tile
+    shape with its ragged last column chunk, and the wide one)."""
+    M, n_nodes, row_off, world = 1500, 4000, 123, 4
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(M, K, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+    hi, lo = ops.split_tf32(b)
+    ref = ops.gemm_tf32x3(a, hi, lo)
+    dst = [torch.full((n_nodes, N), float("nan"), device="cuda") for _ in range(world)]
+    ops.gemm_tf32x3_bcast(a, hi, lo, [d.data_ptr() for d in dst], row_off, N)
+    for q in range(world):
+        assert torch.equal(dst[q][row_off:row_off + M], ref)
+        assert torch.isnan(dst[q][:row_off]).all() and torch.isnan(dst[q][row_off + M:]).all()
