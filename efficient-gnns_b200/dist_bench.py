@@ -154,8 +154,14 @@ def run(args):
                     "cuda_graph": bool(graph), "exchange_bytes_received_per_rank_per_step": ex,
                     "nvlink_floor_ms": ex / 770e9 * 1e3,
                     "aggregations_executed": tr.aggregations_per_step()},
-                "roofline": {"bound": "nvlink+hbm", "note": "multi-GPU point: the all-gathers bound the step; see "
-                             "nvlink_floor_ms (bytes received per rank / 770 GB/s measured peer bandwidth)",
+                "roofline": {"bound": "nvlink+hbm",
+                             "note": ("multi-GPU point. achieved = bytes each rank RECEIVES over NVLink per step / step time against the "
+                                      "measured 770 GB/s peer bandwidth (nvlink_floor_ms = the same bytes at that rate). For the hybrid "
+                                      "layout the exchanges are stores issued by the producing kernels' epilogues and the floor is far "
+                                      "below the step: the limiter is the per-rank compute that does not shrink with N (every rank "
+                                      "walks all edges at width K/N; profiles/r2_hybrid_rank_w*_summary.txt), not the links")
+                             if mode.startswith("hybrid") else
+                             "multi-GPU point: the all-gathers bound the step; see nvlink_floor_ms",
                              "achieved": ex / (ms_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
                              "frac": ex / (ms_step * 1e-3) / 1e9 / 770.0, "traffic": None},
                 "cpu_baseline": None,

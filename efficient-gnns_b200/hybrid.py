@@ -214,9 +214,12 @@ class HybridGCNTrainer(GCNStudentTrainer):
     """One rank of the hybrid-layout GCN student; same step semantics as GCNStudentTrainer (engine.py)."""
 
     def __init__(self, adj: SparseTensor, dims: List[int], group=None, exchange: str = "peer", _fake=None, fuse_r2c: bool = True,
-                 fuse_c2r: bool = True, **kw):
+                 fuse_c2r: bool = True, fuse_gather: bool = False, **kw):
         self.group = group
         self.fuse_r2c, self.fuse_c2r = bool(fuse_r2c), bool(fuse_c2r)
+        # the narrow row all-gather inside the GEMM epilogue (b200gnn_gemm_tf32x3_bcast_f32): measured neutral on 2 GPUs
+        # (1.85 vs 1.81 ms/step), P x the stores from a 1-wave GEMM — off unless asked for
+        self.fuse_gather = bool(fuse_gather)
         if _fake is not None:                       # (rank, world) of a pretended run: exchange="null" only
             assert exchange == "null"
             self.rank, self.world = _fake
@@ -382,7 +385,7 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 continue
             src = x_in if l == 0 else inp
             self._layer_in[l] = src
-            fused_gather = (not self.col_mode[k]) and isinstance(self.ex, PeerExchange) and self.tc_gemm and self.fuse_r2c and k % 4 == 0
+            fused_gather = (not self.col_mode[k]) and isinstance(self.ex, PeerExchange) and self.tc_gemm and self.fuse_gather and k % 4 == 0
             if self.col_mode[k] and self._fusable(k):
                 self._linear_r2c(l, src, f"Hc{l}")           # GEMM epilogue = the R->C exchange
             elif fused_gather:                              # GEMM epilogue = the row all-gather of the narrow operand
