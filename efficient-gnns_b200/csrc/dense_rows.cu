@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 }
 
 // pass 2: dY = gamma*invstd * (dz - mean(dz) - xhat*mean(dz*xhat)); optional partial column sums of dY
-// (gradient of the conv bias in front of the BatchNorm).
+// (gradient of the conv bias in front of the BatchNorm).  DZ: dOut already holds dz (the fused input-gradient GEMM,
+// b200gnn_gemm_tf32x3_bnbwd_f32, stored it) — Xout is not read.
+template <bool DZ>
 __global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_apply_kernel(
     const float* __restrict__ dOut, const float* __restrict__ Xout, const float* __restrict__ Y,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef, int64_t n_rows,
@@ -333,12 +335,18 @@ __global__ void __launch_bounds__(ROWS_THREADS) bn_act_bwd_apply_kernel(
     const float4 c1 = ld4(coef + 4 * m.cv), c2 = ld4(coef + K + 4 * m.cv), c3 = ld4(coef + 2 * K + 4 * m.cv);
     for (int64_t r = r0 + m.rg; r < r1; r += m.rows_per_iter) {
       const size_t o = (size_t)r * K + 4 * m.cv;
-      const float4 g = ld4s(dOut + o), x = ld4s(Xout + o), y = ld4s(Y + o);
+      float4 g = ld4s(dOut + o);
+      const float4 y = ld4s(Y + o);
+      if (!DZ) {
+        const float4 x = ld4s(Xout + o);
+        g.x = x.x > 0.f ? g.x * inv_keep : 0.f; g.y = x.y > 0.f ? g.y * inv_keep : 0.f;
+        g.z = x.z > 0.f ? g.z * inv_keep : 0.f; g.w = x.w > 0.f ? g.w * inv_keep : 0.f;
+      }
       float4 d;
-      d.x = c1.x * ((x.x > 0.f ? g.x * inv_keep : 0.f) - c2.x - (y.x - mu.x) * is.x * c3.x);
-      d.y = c1.y * ((x.y > 0.f ? g.y * inv_keep : 0.f) - c2.y - (y.y - mu.y) * is.y * c3.y);
-      d.z = c1.z * ((x.z > 0.f ? g.z * inv_keep : 0.f) - c2.z - (y.z - mu.z) * is.z * c3.z);
-      d.w = c1.w * ((x.w > 0.f ? g.w * inv_keep : 0.f) - c2.w - (y.w - mu.w) * is.w * c3.w);
+      d.x = c1.x * (g.x - c2.x - (y.x - mu.x) * is.x * c3.x);
+      d.y = c1.y * (g.y - c2.y - (y.y - mu.y) * is.y * c3.y);
+      d.z = c1.z * (g.z - c2.z - (y.z - mu.z) * is.z * c3.z);
+      d.w = c1.w * (g.w - c2.w - (y.w - mu.w) * is.w * c3.w);
       st4(dY + o, d);
       s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
     }
@@ -536,13 +544,15 @@ extern "C" int b200gnn_bn_act_bwd_reduce_f32(const float* dOut, const float* Xou
 }
 
 // phase 2: sums[sum_slots][2][K] (local partials, or one slot of globally reduced sums) + the normalisation count
-// n_norm (global row count) -> dgamma, dbeta, dY (and dbias = column sums of the LOCAL dY rows if requested)
+// n_norm (global row count) -> dgamma, dbeta, dY (and dbias = column sums of the LOCAL dY rows if requested).
+// Xout == NULL: dOut already holds dz = dOut * [Xout > 0] / (1-p) (written by b200gnn_gemm_tf32x3_bnbwd_f32, whose
+// partial buffer is then `sums`); dY may alias dOut.
 extern "C" int b200gnn_bn_act_bwd_apply_f32(const float* dOut, const float* Xout, const float* Y, const float* mean,
                                             const float* invstd, const float* gamma, const float* sums,
                                             int64_t sum_slots, int64_t n_norm, int64_t n_rows, int64_t K, float p,
                                             float* dY, float* dgamma, float* dbeta, float* dbias, float* partial,
                                             int64_t slots, float* coef, void* stream) {
-  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Xout || !Y || !mean || !invstd || !gamma || !sums || !dY ||
+  if (!rows_ok(n_rows, K) || n_rows == 0 || !dOut || !Y || !mean || !invstd || !gamma || !sums || !dY ||
       !dgamma || !dbeta || !partial || !coef || slots < 1 || sum_slots < 1 || n_norm < 1 || p < 0.f || p >= 1.f)
     return B200GNN_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -552,8 +562,12 @@ extern "C" int b200gnn_bn_act_bwd_apply_f32(const float* dOut, const float* Xout
   bn_bwd_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(sums, (int)sum_slots, (int)K, n_norm, gamma,
                                                                               invstd, dgamma, dbeta, coef);
   if ((rc = check_launch())) return rc;
-  bn_act_bwd_apply_kernel<<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, coef, n_rows, (int)K,
-                                                                 inv_keep, dY, dbias ? partial : nullptr, (int)slots);
+  if (Xout)
+    bn_act_bwd_apply_kernel<false><<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, Xout, Y, mean, invstd, coef, n_rows, (int)K,
+                                                                          inv_keep, dY, dbias ? partial : nullptr, (int)slots);
+  else
+    bn_act_bwd_apply_kernel<true><<<(int)slots, ROWS_THREADS, smem, st>>>(dOut, nullptr, Y, mean, invstd, coef, n_rows, (int)K,
+                                                                         inv_keep, dY, dbias ? partial : nullptr, (int)slots);
   if ((rc = check_launch())) return rc;
   if (dbias) {
     colsum_finalize_kernel<<<(int)((K + FIN_COLS - 1) / FIN_COLS), 256, 0, st>>>(partial, (int)slots, (int)K, dbias);

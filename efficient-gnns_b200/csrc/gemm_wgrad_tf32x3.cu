@@ -21,11 +21,14 @@ namespace wgrad {
 using namespace tc;
 
 constexpr int BKN = 16;                       // nodes per pipeline stage (two K=8 MMA steps)
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 8;
 constexpr int THREADS = 384;
-constexpr int OPER_BYTES = 8 * BKN * 128;     // 16 KB: up to 256 columns = 8 groups x 16 nodes x 128 B
-constexpr int STAGE_BYTES = 4 * OPER_BYTES;   // X_hi, X_lo, G_hi, G_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int GROUP_BYTES = BKN * 128;        // 2 KB: one 32-column group of one operand, 16 nodes x 128 B
+// A stage holds X_hi, X_lo ([Kin/32] groups each) and G_hi, G_lo ([Npad/32] groups each) back to back; the pool is cut into
+// as many stages as fit (3 at 256x256 = 64 KB per stage, 4 at 128x256, 5 at 256x64): the narrow shapes are bound by the
+// latency of the TMA -> split -> MMA -> free chain per stage, which only depth hides.
+constexpr int POOL_BYTES = 5 * 40 * 1024;
+constexpr int SMEM_BYTES = POOL_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 512;
 // The tensor core rounds its fp32 accumulator towards zero on every accumulate (tools/probe_accum.py): a CTA that
 // chains its whole node range (~430 MMAs at ARXIV size) ends 1.3e-5 low; the loss depends on HOW OFTEN the large
@@ -51,19 +54,24 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
 struct Params {
   float* partial;   // [grid][Kin][Npad],  Npad = Nout rounded up to 32 (TMA zero-fills the missing columns)
   int32_t Nn, Kin, Nout, Npad, num_kb;
+  int32_t mode;     // 0 automatic; A/B knobs (b200gnn_wgrad_set_mode): 1 = drains only, 2 = one chain (round-1 behaviour)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + POOL_BYTES);
   uint64_t* full = bars;
-  uint64_t* split = bars + STAGES;
-  uint64_t* empty = bars + 2 * STAGES;
-  uint64_t* acc_full = bars + 3 * STAGES;
+  uint64_t* split = bars + MAX_STAGES;
+  uint64_t* empty = bars + 2 * MAX_STAGES;
+  uint64_t* acc_full = bars + 3 * MAX_STAGES;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  const int xg = p.Kin / 32, gg = p.Npad / 32;               // 32-column groups of X and G
+  const int X_BYTES = xg * GROUP_BYTES, G_BYTES = gg * GROUP_BYTES;
+  const int STAGE_BYTES = 2 * (X_BYTES + G_BYTES);
+  const int STAGES = min(MAX_STAGES, POOL_BYTES / STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -87,13 +95,12 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int kb1 = (int)((int64_t)p.num_kb * (blockIdx.x + 1) / gridDim.x);
   const int mtiles = p.Kin / 128;
   const int len = kb1 - kb0;
-  const bool sep = (mtiles == 1) || (p.Npad <= 128);   // room for a separate correction accumulator
+  const bool sep = p.mode == 0 && ((mtiles == 1) || (p.Npad <= 128));   // room for a separate correction accumulator
   const uint32_t corr_off = mtiles == 1 ? 256u : 128u;
-  int nd = sep ? 1 : (len + DRAIN_KB - 1) / DRAIN_KB;  // accumulator drains of this CTA (>= 1 when it has work)
+  int nd = (sep || p.mode == 2) ? 1 : (len + DRAIN_KB - 1) / DRAIN_KB;  // accumulator drains of this CTA (>= 1 when it has work)
   if (nd < 1) nd = 1;
   if (nd > len && len > 0) nd = len;
-  const int xg = p.Kin / 32, gg = p.Npad / 32;               // 32-column groups of X and G
-  const uint32_t tx_bytes = (uint32_t)(xg + gg) * BKN * 128;
+  const uint32_t tx_bytes = (uint32_t)(X_BYTES + G_BYTES);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -102,8 +109,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full[s], tx_bytes);
-        for (int g = 0; g < xg; ++g) tma_load_2d(&tmX, &full[s], st + g * (BKN * 128), g * 32, kb * BKN);
-        for (int g = 0; g < gg; ++g) tma_load_2d(&tmG, &full[s], st + 2 * OPER_BYTES + g * (BKN * 128), g * 32, kb * BKN);
+        for (int g = 0; g < xg; ++g) tma_load_2d(&tmX, &full[s], st + g * GROUP_BYTES, g * 32, kb * BKN);
+        for (int g = 0; g < gg; ++g) tma_load_2d(&tmG, &full[s], st + 2 * X_BYTES + g * GROUP_BYTES, g * 32, kb * BKN);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -123,11 +130,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
           for (int kg = 0; kg < BKN / 8; ++kg) {
-            const uint64_t g_hi = make_desc_mn(st + 2 * OPER_BYTES + kg * 1024);
-            const uint64_t g_lo = make_desc_mn(st + 3 * OPER_BYTES + kg * 1024);
+            const uint64_t g_hi = make_desc_mn(st + 2 * X_BYTES + kg * 1024);
+            const uint64_t g_lo = make_desc_mn(st + 2 * X_BYTES + G_BYTES + kg * 1024);
             for (int mt = 0; mt < mtiles; ++mt) {
               const uint32_t xoff = (uint32_t)(mt * 4 * BKN * 128 + kg * 1024);
-              const uint64_t x_hi = make_desc_mn(st + xoff), x_lo = make_desc_mn(st + OPER_BYTES + xoff);
+              const uint64_t x_hi = make_desc_mn(st + xoff), x_lo = make_desc_mn(st + X_BYTES + xoff);
               const uint32_t dt = tmem_base + (uint32_t)(mt * 256);
               const uint32_t first = (kb != d0) | (kg != 0);
               if (sep) {
@@ -154,9 +161,9 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&full[s], ph);
       uint4* xh = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES);
-      uint4* xl = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + OPER_BYTES);
-      uint4* gh = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + 2 * OPER_BYTES);
-      uint4* gl = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + 3 * OPER_BYTES);
+      uint4* xl = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + X_BYTES);
+      uint4* gh = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + 2 * X_BYTES);
+      uint4* gl = reinterpret_cast<uint4*>(smem + s * STAGE_BYTES + 2 * X_BYTES + G_BYTES);
       for (int o = t; o < nx; o += 128) { const uint4 v = xh[o]; uint4 h, l; split4(v, h, l); xh[o] = h; xl[o] = l; }
       for (int o = t; o < ng; o += 128) { const uint4 v = gh[o]; uint4 h, l; split4(v, h, l); gh[o] = h; gl[o] = l; }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -186,8 +193,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           for (int j = 0; j < 8; ++j) {
             float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                    __uint_as_float(r[4 * j + 3]));
-            if (d > 0) { const float4 o = dst[j]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }   // same thread wrote it
-            dst[j] = v;
+            if (d > 0)      // later drains ADD to the slot (same thread, same address: ordered); no read-back latency
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
+            else
+              dst[j] = v;
           }
         }
       }
@@ -252,6 +262,9 @@ static bool make_map_mn(CUtensorMap* m, const float* base, int64_t rows, int64_t
 
 using namespace b200gnn;
 
+static int g_wgrad_mode = 0;
+extern "C" void b200gnn_wgrad_set_mode(int mode) { g_wgrad_mode = mode; }
+
 extern "C" int64_t b200gnn_wgrad_workspace_floats(int64_t Kin, int64_t Nout) {
   if (Kin <= 0 || Nout <= 0) return B200GNN_ERR_BAD_ARG;
   return 148 * Kin * ((Nout + 31) / 32 * 32);
@@ -281,6 +294,7 @@ extern "C" int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const 
   p.partial = workspace; p.Nn = (int32_t)Nn; p.Kin = (int32_t)Kin; p.Nout = (int32_t)Nout;
   p.Npad = (int32_t)((Nout + 31) / 32 * 32);
   p.num_kb = (int32_t)((Nn + wgrad::BKN - 1) / wgrad::BKN);
+  p.mode = g_wgrad_mode;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -53,7 +53,7 @@ class GCNStudentTrainer:
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
                  alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
                  aggregate_first: Optional[bool] = None, tensor_core_gemm: bool = True, overlap_wgrad: bool = True,
-                 _prebuilt_graph: Optional[CsrGraph] = None, _rows_alloc: Optional[int] = None):
+                 fuse_row_passes: bool = True, _prebuilt_graph: Optional[CsrGraph] = None, _rows_alloc: Optional[int] = None):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         self.device = adj.device
         self.dims, self.L = list(dims), len(dims) - 1
@@ -148,6 +148,11 @@ class GCNStudentTrainer:
         self.stat_part = [torch.empty(slots_spmm, 2, dims[l + 1], device=dev) for l in range(self.L - 1)]
         self.bn = [torch.empty(4, dims[l + 1], device=dev) for l in range(self.L - 1)]   # mean, invstd, scale, shift
         self.rs = ops.rows_slots(N)
+        # Row passes fused into GEMM epilogues: the layer-0 BatchNorm statistics come out of the layer-0 GEMM
+        # and pass 1 of every BatchNorm/ReLU/dropout backward out of the input-gradient GEMM that produces its dOut.
+        self.fuse_rows = bool(fuse_row_passes) and self.tc_gemm
+        self._gemm_part = {k: torch.empty(ops.gemm_stat_slots(N, k), 2, k, device=dev)
+                           for k in set(dims[1:-1]) if self.fuse_rows and ops.gemm_stats_supported(k)}
         self.loss_out = self._grads_buf[self.n_par_pad:self.n_par_pad + 3]
         self.kd_part = torch.empty(2 * int(lib.load().b200gnn_kd_partials(N)), device=dev)
         self._graph = None
@@ -214,14 +219,21 @@ class GCNStudentTrainer:
             last = l == self.L - 1
             if l == 0 and self.agg_first:
                 ops.spmm_csr(self.G, x, "sum", out=self.AX)
-                self._linear(0, self.AX, self.Y[0], bias=self.b[0])
                 if training:
-                    ops.col_stats(self.Y[0], partial=self._part(self.dims[1]))
-                    ops.bn_finalize(self._part(self.dims[1]), self.N, self.gamma[0], self.beta[0], self.bn_eps,
+                    gp = self._gemm_part.get(self.dims[1])
+                    if gp is not None:                               # statistics of Y0 from the GEMM epilogue
+                        hi, lo = ops.split_tf32(self.W[0], transpose=True, hi=self.Wt_split[0][0], lo=self.Wt_split[0][1])
+                        ops.gemm_tf32x3_stats(self.AX, hi, lo, self.b[0], self.Y[0], gp)
+                        part = gp
+                    else:
+                        self._linear(0, self.AX, self.Y[0], bias=self.b[0])
+                        part = ops.col_stats(self.Y[0], partial=self._part(self.dims[1]))
+                    ops.bn_finalize(part, self.N, self.gamma[0], self.beta[0], self.bn_eps,
                                     self.bn_momentum, self.running_mean[0], self.running_var[0], out=self.bn[0])
                     ops.affine_relu_dropout(self.Y[0], self.bn[0][2], self.bn[0][3], True, self.p, self.seed, 0,
                                             out=self.A[0], step_dev=self.step_count, step_mul=self.L)
                 else:
+                    self._linear(0, self.AX, self.Y[0], bias=self.b[0])
                     scale = self.gamma[0] * torch.rsqrt(self.running_var[0] + self.bn_eps)
                     shift = self.beta[0] - self.running_mean[0] * scale
                     ops.affine_relu_dropout(self.Y[0], scale, shift, True, 0.0, out=self.A[0])
@@ -257,20 +269,32 @@ class GCNStudentTrainer:
                 continue
             ops.spmm_csr(self.Gt, self.dY[l], "sum", out=self.dH[l])
             d_prev = self.dA[l - 1] if l > 0 else None
+            gp = self._gemm_part.get(self.dims[l]) if l > 0 else None
             if l > 0:
-                if d_out_feat is not None and l == self.L - 1:
+                acc = d_out_feat is not None and l == self.L - 1
+                if acc:
                     # the auxiliary loss's gradient w.r.t. out_feat is the starting value the input-gradient GEMM adds to
                     d_prev = d_out_feat
-                    self._linear_dgrad(l, self.dH[l], d_prev, accumulate=True)
+                if gp is not None:
+                    # dgrad GEMM whose epilogue masks by the ReLU/dropout pattern, stores dz and reduces the two BatchNorm
+                    # backward column sums: pass 1 of the block's backward costs no sweep of its own
+                    hi, lo = ops.split_tf32(self.W[l], transpose=False, hi=self.W_split[l][0], lo=self.W_split[l][1])
+                    ops.gemm_tf32x3_bnbwd(self.dH[l], hi, lo, d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0],
+                                          self.bn[l - 1][1], self.p, gp, accumulate=acc)
                 else:
-                    self._linear_dgrad(l, self.dH[l], d_prev)
+                    self._linear_dgrad(l, self.dH[l], d_prev, accumulate=acc)
             self._wgrad_async(l, inp, self.dH[l])                      # forks after the dgrad GEMM (both want the whole SM)
             if l > 0:
                 k = self.dims[l]
                 part = self._part(k)
-                ops.bn_act_bwd(d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
-                               self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
-                               d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
+                if gp is not None:
+                    ops.bn_act_bwd_apply(d_prev, None, self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1], self.gamma[l - 1],
+                                         gp, self.N, self.p, self.dY[l - 1], self.ggamma[l - 1], self.gbeta[l - 1],
+                                         self.gb[l - 1], part, self._coef(k))
+                else:
+                    ops.bn_act_bwd(d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
+                                   self.gamma[l - 1], self.p, d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1],
+                                   d_beta=self.gbeta[l - 1], d_bias=self.gb[l - 1], partial=part, coef=self._coef(k))
         self._wgrad_join()
 
     def _wgrad_async(self, l: int, inp: torch.Tensor, d_out: torch.Tensor):

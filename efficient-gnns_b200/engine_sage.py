@@ -30,7 +30,8 @@ from .sparse import CsrGraph, SparseTensor
 
 class SAGEStudentTrainer:
     def __init__(self, adj: SparseTensor, dims: List[int], dropout: float = 0.5, lr: float = 0.01, seed: int = 0,
-                 alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+                 alpha: float = 0.9, kd_T: float = 4.0, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
+                 fuse_row_passes: bool = True):
         assert adj.is_cuda(), "the engine runs on a CUDA device"
         for d in dims:
             assert d % 4 == 0 and d <= 1024, "layer widths must be multiples of 4 (128-bit rows)"
@@ -83,6 +84,9 @@ class SAGEStudentTrainer:
         self.dA = [buf(dims[l + 1]) for l in range(self.L - 1)]
         self.bn = [torch.empty(4, dims[l + 1], device=dev) for l in range(self.L - 1)]
         self.rs = ops.rows_slots(N)
+        # BatchNorm statistics / backward reductions taken in GEMM epilogues (engine.py)
+        self._gemm_part = {k: torch.empty(ops.gemm_stat_slots(N, k), 2, k, device=dev)
+                           for k in set(self.dims[1:-1]) if fuse_row_passes and ops.gemm_stats_supported(k)}
         self._static: Dict[str, torch.Tensor] = {}
         self.kd_part = torch.empty(2 * int(lib.load().b200gnn_kd_partials(N)), device=dev)
         self.split = {}
@@ -174,11 +178,15 @@ class SAGEStudentTrainer:
             hi, lo = self._split(self.Wl[l], False, f"wl{l}")            # GEMM wants B as [N_out, K]: nn.Linear's own layout
             ops.gemm_tf32x3(self.M[l], hi, lo, bias=self.bl[l], out=self.Y[l])
             hi, lo = self._split(self.Wr[l], False, f"wr{l}")
-            ops.gemm_tf32x3(inp, hi, lo, out=self.Y[l], accumulate=True)
+            gp = self._gemm_part.get(k) if (training and l < self.L - 1) else None
+            if gp is not None:                       # BatchNorm statistics of the layer output from this GEMM's epilogue
+                ops.gemm_tf32x3_stats(inp, hi, lo, None, self.Y[l], gp, accumulate=True)
+            else:
+                ops.gemm_tf32x3(inp, hi, lo, out=self.Y[l], accumulate=True)
             if l == self.L - 1:
                 break
             if training:
-                part = ops.col_stats(self.Y[l], partial=self._part(k))
+                part = gp if gp is not None else ops.col_stats(self.Y[l], partial=self._part(k))
                 ops.bn_finalize(part, self.N, self.gamma[l], self.beta[l], self.bn_eps, self.bn_momentum, self.running_mean[l],
                                 self.running_var[l], out=self.bn[l])
                 ops.affine_relu_dropout(self.Y[l], self.bn[l][2], self.bn[l][3], True, self.p, self.seed, l, out=self.A[l],
@@ -204,11 +212,21 @@ class SAGEStudentTrainer:
             ops.gemm_tf32x3(self.dY[l], hi, lo, out=self.dM[l])
             d_prev = self.dA[l - 1]
             ops.spmm_csr(self.Gt, self.dM[l], "sum", out=d_prev)
-            hi, lo = self._split(self.Wr[l], True, f"wrT{l}")
-            ops.gemm_tf32x3(self.dY[l], hi, lo, out=d_prev, accumulate=True)
             if d_out_feat is not None and l == self.L - 1:
                 d_prev.add_(d_out_feat)
+            hi, lo = self._split(self.Wr[l], True, f"wrT{l}")
             kp = self.dims[l]
+            gp = self._gemm_part.get(kp)
+            if gp is not None:
+                # the last contribution to dOut is an accumulating GEMM: its epilogue masks, stores dz and reduces the BatchNorm
+                # backward column sums (pass 1 of the block's backward)
+                ops.gemm_tf32x3_bnbwd(self.dY[l], hi, lo, d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1],
+                                      self.p, gp, accumulate=True)
+                ops.bn_act_bwd_apply(d_prev, None, self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1], self.gamma[l - 1], gp,
+                                     self.N, self.p, self.dY[l - 1], self.ggamma[l - 1], self.gbeta[l - 1], None, self._part(kp),
+                                     self._coef(kp))
+                continue
+            ops.gemm_tf32x3(self.dY[l], hi, lo, out=d_prev, accumulate=True)
             ops.bn_act_bwd(d_prev, self.A[l - 1], self.Y[l - 1], self.bn[l - 1][0], self.bn[l - 1][1], self.gamma[l - 1], self.p,
                            d_y=self.dY[l - 1], d_gamma=self.ggamma[l - 1], d_beta=self.gbeta[l - 1], partial=self._part(kp),
                            coef=self._coef(kp), want_dbias=False)

@@ -241,9 +241,26 @@ def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = 0, dim_size: Opti
     if reduce not in ("sum", "add", "mean"):
         raise NotImplementedError(f"scatter reduce={reduce!r}")
     n = int(index.max()) + 1 if dim_size is None else dim_size
+    return ops.matmul(_selection_matrix(index, n), src, "mean" if reduce == "mean" else "sum")
+
+
+_SEL_CACHE: dict = {}
+
+
+def _selection_matrix(index: torch.Tensor, n: int) -> SparseTensor:
+    """The [n x E] selection matrix of a scatter index, with its sort, CSR/CSC views and chunk/hub plans, cached per index
+    tensor (RGCNConv scatters over the same 7 relation masks every layer and every step: mag_pyg/gnn.py:54-68).  The cache
+    keeps a reference to the index tensor, so its address cannot be recycled for different contents while the entry lives."""
+    key = (index.data_ptr(), int(index.numel()), index._version, n, str(index.device))
+    hit = _SEL_CACHE.get(key)
+    if hit is not None and hit[0] is index:
+        return hit[1]
     E = index.numel()
     sel = SparseTensor(row=index, col=torch.arange(E, device=index.device), sparse_sizes=(n, E), is_sorted=False)
-    return ops.matmul(sel, src, "mean" if reduce == "mean" else "sum")
+    if len(_SEL_CACHE) > 64:
+        _SEL_CACHE.clear()
+    _SEL_CACHE[key] = (index, sel)
+    return sel
 
 
 class MessagePassing(torch.nn.Module):

@@ -292,6 +292,45 @@ def gemm_tf32x3(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: O
     return out
 
 
+def gemm_stat_slots(m: int, n: int) -> int:
+    """Slots of the [slots, 2, n] partial buffer the statistics-fused GEMMs fill."""
+    return int(lib.load().b200gnn_gemm_stat_slots(m, n))
+
+
+def gemm_stats_supported(n: int) -> bool:
+    return n % 32 == 0 and 48 < n <= 256
+
+
+def gemm_tf32x3_stats(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                      partial: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """out = a @ b^T + bias (or out += a @ b^T) with the BatchNorm batch statistics of the final ``out`` reduced in the epilogue:
+    partial[slots, 2, N] = per-slot (column sum, column sum of squares) — feed to ``bn_finalize`` (no sweep over out)."""
+    M, K = a.shape
+    N = b_hi.shape[0]
+    lib.check(lib.load().b200gnn_gemm_tf32x3_stats_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                       b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K, _f32(bias, "bias"),
+                                                       int(accumulate), _f32(partial, "partial"), partial.shape[0], lib.stream_ptr()),
+              "gemm_tf32x3_stats_f32")
+    return out
+
+
+def gemm_tf32x3_bnbwd(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, out: torch.Tensor, x_out: torch.Tensor,
+                      y: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, p: float, partial: torch.Tensor,
+                      accumulate: bool = False) -> torch.Tensor:
+    """Input-gradient GEMM with pass 1 of the BatchNorm/ReLU/dropout backward in its epilogue: d_out = a @ b^T (+ out),
+    and what is STORED to ``out`` is dz = d_out * [x_out > 0] / (1-p); partial[slots, 2, N] = per-slot (sum dz, sum dz*xhat).
+    Follow with ``bn_act_bwd_apply(out, None, y, ..., sums=partial, ...)``."""
+    M, K = a.shape
+    N = b_hi.shape[0]
+    assert out.shape == x_out.shape == y.shape and out.stride(0) == x_out.stride(0) == y.stride(0)
+    lib.check(lib.load().b200gnn_gemm_tf32x3_bnbwd_f32(_f32(a, "a"), a.stride(0), _f32(b_hi, "b_hi"), _f32(b_lo, "b_lo"),
+                                                       b_hi.stride(0), _f32(out, "out"), out.stride(0), M, N, K, int(accumulate),
+                                                       _f32(x_out, "x_out"), _f32(y, "y"), _f32(mean, "mean"),
+                                                       _f32(invstd, "invstd"), float(p), _f32(partial, "partial"),
+                                                       partial.shape[0], lib.stream_ptr()), "gemm_tf32x3_bnbwd_f32")
+    return out
+
+
 def gemm_tf32x3_scatter(a: torch.Tensor, b_hi: torch.Tensor, b_lo: torch.Tensor, dst_ptrs, row_off: int,
                         bias: Optional[torch.Tensor] = None) -> None:
     """a[M,K] @ b[N,K]^T with column block q of the result stored to the [*, N/world] matrix at raw device address

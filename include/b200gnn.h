@@ -214,6 +214,9 @@ int b200gnn_bn_act_bwd_apply_f32(const float* dOut, const float* Xout,
                                  float p, float* dY, float* dgamma,
                                  float* dbeta, float* dbias, float* partial,
                                  int64_t slots, float* coef, void* stream);
+/* Xout == NULL in b200gnn_bn_act_bwd_apply_f32: dOut already holds
+ * dz = dOut * [Xout > 0] / (1-p), as stored by b200gnn_gemm_tf32x3_bnbwd_f32
+ * (whose partial buffer is then `sums`); dY may alias dOut. */
 /* out[K2] = sum over slots of partial[slot][K2] (K2 = 2*K for statistics) */
 int b200gnn_partial_reduce_f32(const float* partial, int64_t slots, int64_t K2,
                                float* out, void* stream);
@@ -267,6 +270,28 @@ int b200gnn_gemm_tf32x3_f32(const float* A, int64_t lda, const float* B_hi,
 int b200gnn_gemm_tf32x3_acc_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                 int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                                 void* stream);
+/* Row passes fused into the GEMM epilogue (the reference runs conv -> BatchNorm1d -> ReLU -> dropout as
+ * separate full-matrix ops, arxiv_pyg/gnn.py:47-50, and autograd walks them again backwards).  Each epilogue warp keeps
+ * running column sums over the tiles of its CTA and stores them once: partial[slots][2][N], slots >=
+ * b200gnn_gemm_stat_slots(M, N), fixed summation order (deterministic).  N a multiple of 32, 48 < N <= 256, ldc % 4 == 0.
+ *   _stats_f32 : C = A·B^T + bias (accumulate: C += A·B^T, no bias — SAGEConv's lin_l(mean) + lin_r(x)) and partial = per-slot (sum C, sum C^2) over rows — the BatchNorm batch statistics of C,
+ *                input of b200gnn_bn_finalize_f32 (replaces the b200gnn_col_stats_f32 sweep).
+ *   _bnbwd_f32 : the input-gradient GEMM of the layer BEHIND a BatchNorm->ReLU->dropout block with pass 1 of that block's
+ *                backward in the epilogue: dOut = A·B^T (+ C if accumulate); dz = dOut * [Xout > 0] / (1-p) is what is STORED
+ *                to C, partial = per-slot (sum dz, sum dz*xhat), xhat = (Y-mean)*invstd (replaces
+ *                b200gnn_bn_act_bwd_reduce_f32; follow with b200gnn_bn_act_bwd_apply_f32(dOut = C, Xout = NULL, sums =
+ *                partial)).  Xout, Y: [M, ldc] like C. */
+int64_t b200gnn_gemm_stat_slots(int64_t M, int64_t N);
+/* A/B knob for measurements: 0 automatic (Xout / Y of _bnbwd_f32 staged through TMA when N % 128 == 0), 2 = always the
+ * register path. */
+void b200gnn_gemm_set_bnbwd_variant(int v);
+int b200gnn_gemm_tf32x3_stats_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                                  int accumulate, float* partial, int64_t slots, void* stream);
+int b200gnn_gemm_tf32x3_bnbwd_f32(const float* A, int64_t lda, const float* B_hi, const float* B_lo, int64_t ldb,
+                                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
+                                  const float* Xout, const float* Y, const float* mean, const float* invstd, float p_drop,
+                                  float* partial, int64_t slots, void* stream);
 /* Same GEMM with the R->C layout exchange of the multi-GPU engine fused into the epilogue: output columns
  * [q*kc, (q+1)*kc), kc = N/world (a multiple of 32), are stored to C_ptrs[q][(row_off + m)*kc + ...] — C_ptrs is a HOST array
  * of `world` device pointers (the ranks' [N_nodes, kc] buffers, peer-mapped), so the tile results cross NVLink as they are
@@ -289,6 +314,9 @@ int b200gnn_gemm_wgrad_tf32x3_f32(const float* X, int64_t ldx, const float* G,
                                   int64_t ldg, float* dW, int64_t Nn,
                                   int64_t Kin, int64_t Nout, float* workspace,
                                   void* stream);
+/* A/B knob for measurements: 0 automatic (separate correction accumulators / drains against the accumulator's
+ * round-towards-zero), 1 drains only, 2 one accumulation chain per CTA (round-1 behaviour, 1e-5-level gradient error). */
+void b200gnn_wgrad_set_mode(int mode);
 
 /* ------------------------------------------------------------------ *
  * Feature-distillation criteria (arxiv_pyg/criterion.py): row / pair passes.

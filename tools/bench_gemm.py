@@ -41,18 +41,49 @@ def main():
                               hbm_GBps=(M * K + M * N) * 4 / t_tc / 1e6, rel_err=err)), flush=True)
 
 
+def bnbwd():
+    """Input-gradient GEMM with the BatchNorm-backward reduction in its epilogue vs GEMM + separate reduce pass."""
+    from efficient_gnns_b200 import lib
+    M, N = 169_343, 256
+    y = torch.randn(M, N, device="cuda")
+    x_out = torch.relu(torch.randn(M, N, device="cuda"))
+    mean, invstd = y.mean(0), (y.var(0, unbiased=False) + 1e-5).rsqrt()
+    out = torch.empty(M, N, device="cuda")
+    part = torch.empty(ops.gemm_stat_slots(M, N), 2, N, device="cuda")
+    part2 = torch.empty(ops.rows_slots(M), 2, N, device="cuda")
+    for K in (40, 256):
+        a = torch.randn(M, K, device="cuda")
+        hi, lo = ops.split_tf32(torch.randn(N, K, device="cuda"))
+        res = dict(kind="bnbwd", M=M, N=N, K=K)
+        res["ms_gemm"] = timeit(lambda: ops.gemm_tf32x3(a, hi, lo, out=out))
+        res["ms_reduce_pass"] = timeit(lambda: ops.bn_act_bwd_reduce(out, x_out, y, mean, invstd, 0.5, part2))
+        for variant, name in ((0, "ms_fused_tma"), (2, "ms_fused_regs")):
+            lib.load().b200gnn_gemm_set_bnbwd_variant(variant)
+            res[name] = timeit(lambda: ops.gemm_tf32x3_bnbwd(a, hi, lo, out, x_out, y, mean, invstd, 0.5, part))
+        lib.load().b200gnn_gemm_set_bnbwd_variant(0)
+        res["GBps_fused_tma"] = (M * K + 3 * M * N) * 4 / res["ms_fused_tma"] / 1e6
+        print(json.dumps(res), flush=True)
+
+
 def wgrad():
+    from efficient_gnns_b200 import lib
     M = 169_343
-    for (K, N) in [(128, 256), (256, 256)]:
+    for mode in (0, 1, 2):
+     lib.load().b200gnn_wgrad_set_mode(mode)
+     for (K, N) in [(128, 256), (256, 256), (256, 40)]:
         x = torch.randn(M, K, device="cuda"); d = torch.randn(M, N, device="cuda")
         out = torch.empty(K, N, device="cuda")
-        ws = torch.empty(148 * K * N, device="cuda")
+        ws = torch.empty(148 * K * ((N + 31) // 32 * 32), device="cuda")
         t_tc = timeit(lambda: ops.gemm_wgrad_tf32x3(x, d, out=out, workspace=ws))
-        t_cb = timeit(lambda: torch.mm(x.t(), d, out=out))
-        print(json.dumps(dict(kind="wgrad", Nn=M, Kin=K, Nout=N, ms_tcgen05=t_tc, ms_cublas_fp32=t_cb,
+        t_cb = timeit(lambda: torch.mm(x.t(), d, out=out)) if mode == 0 else None
+        ref = x.double().t() @ d.double()
+        err = ((out.double() - ref).norm() / ref.norm()).item()
+        print(json.dumps(dict(kind="wgrad", mode=mode, Nn=M, Kin=K, Nout=N, ms_tcgen05=t_tc, ms_cublas_fp32=t_cb, fro_err=err,
                               hbm_GBps=(M * K + M * N) * 4 / t_tc / 1e6)), flush=True)
+    lib.load().b200gnn_wgrad_set_mode(0)
 
 
 if __name__ == "__main__":
     wgrad()
+    bnbwd()
     main()
