@@ -12,8 +12,8 @@ import efficient_gnns_b200  # noqa: E402,F401
 from efficient_gnns_b200 import ops, sparse, synthetic  # noqa: E402
 
 
-def build_adj(n, e, device="cuda", gcn=True):
-    ei = synthetic.skewed_edges(n, e, 0).to(device)
+def build_adj(n, e, device="cuda", gcn=True, p_local=0.0):
+    ei = synthetic.skewed_edges(n, e, 0, p_local).to(device)
     row, col = ei
     perm = (col * n + row).argsort()
     adj = sparse.SparseTensor(row=col[perm], col=row[perm], sparse_sizes=(n, n), is_sorted=True).to_symmetric()
@@ -48,17 +48,19 @@ def main():
     ap.add_argument("--chunks", type=int, nargs="+", default=[128])
     ap.add_argument("--variants", type=int, nargs="+", default=[0])
     ap.add_argument("--out", default="")
+    ap.add_argument("--p-local", type=float, default=0.0, help="fraction of edges redrawn inside the source's id block (locality)")
+    ap.add_argument("--weighted-only", action="store_true")
     a = ap.parse_args()
     S = synthetic.ARXIV
     n = S["num_nodes"]
     res = []
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    adjs = {gcn: build_adj(n, S["num_edges"], gcn=gcn) for gcn in (True, False)}
+    adjs = {gcn: build_adj(n, S["num_edges"], gcn=gcn, p_local=a.p_local) for gcn in ((True,) if a.weighted_only else (True, False))}
     for variant in a.variants:
      ops.set_spmm_variant(variant)
      for thr in a.thresholds:
       for chunk in a.chunks:
-        for gcn in (True, False):
+        for gcn in adjs:
             st = adjs[gcn].storage
             G = st.engine_csr() if gcn else st.engine_csr_unweighted()
             G.build_plan(hub_threshold=thr, seg_len=thr, chunk_nnz=chunk)
@@ -72,7 +74,7 @@ def main():
                 med, best = time_fn(lambda: ops.spmm_csr(G, x, red, out=out), a.iters, flush)
                 alg = 2 * n * K * 4 + nnz * (4 + (4 if gcn else 0)) + (n + 1) * 4
                 gather = nnz * (K * 4 + 8) + n * K * 4
-                rec = dict(kernel="spmm", variant=variant, weighted=gcn, reduce=red, K=K, hub_threshold=thr, chunk_nnz=chunk, n_chunks=G.n_chunks, n_hub=G.n_hub, n_seg=G.n_seg,
+                rec = dict(kernel="spmm", p_local=a.p_local, variant=variant, weighted=gcn, reduce=red, K=K, hub_threshold=thr, chunk_nnz=chunk, n_chunks=G.n_chunks, n_hub=G.n_hub, n_seg=G.n_seg,
                            nnz=nnz, ms_median=med, ms_best=best, alg_GBps=alg / med / 1e6, gather_GBps=gather / med / 1e6,
                            edges_per_s=nnz / med * 1e3)
                 print(json.dumps(rec), flush=True)
