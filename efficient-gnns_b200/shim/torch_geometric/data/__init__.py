@@ -1,45 +1,3 @@
-"""torch_geometric.data.Data: an attribute bag whose .to(device) also moves SparseTensors."""
-import torch
-from efficient_gnns_b200.sparse import SparseTensor
-
-
-class Data:
-    def __init__(self, **kwargs):
-        for k, v in kwargs.items():
-            setattr(self, k, v)
-
-    @property
-    def num_nodes(self):
-        if getattr(self, "_num_nodes", None) is not None:
-            return self._num_nodes
-        return self.x.size(0)
-
-    @num_nodes.setter
-    def num_nodes(self, v):
-        self._num_nodes = v
-
-    @property
-    def num_features(self):
-        return self.x.size(1)
-
-    def to(self, device, *a, **k):
-        for name, v in list(self.__dict__.items()):
-            if isinstance(v, (torch.Tensor, SparseTensor)):
-                setattr(self, name, v.to(device))
-        return self
-
-    def __repr__(self):
-        return "Data(" + ", ".join(f"{k}={tuple(v.shape) if isinstance(v, torch.Tensor) else v}" for k, v in self.__dict__.items()) + ")"
-
-
-def _unavailable(name):
-    class _U:
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"torch_geometric.data.{name}: sampling / mini-batch loaders are outside the "
-                                      "full-batch hot path (SURVEY.md §8f rank 4)")
-    _U.__name__ = name
-    return _U
-
-
-GraphSAINTRandomWalkSampler = _unavailable("GraphSAINTRandomWalkSampler")
-DataLoader = _unavailable("DataLoader")
+"""torch_geometric.data: Data (attribute bag) and the device-side mini-batch loaders."""
+from efficient_gnns_b200.graphdata import Data  # noqa: F401
+from efficient_gnns_b200.sampling import Batch, DataLoader, GraphSAINTRandomWalkSampler  # noqa: F401

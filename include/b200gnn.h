@@ -515,6 +515,25 @@ int b200gnn_graph_coalesce_i64(const int64_t* row, const int64_t* col, int64_t n
                                int64_t n_cols, int64_t* out_row, int64_t* out_col, int32_t* src_out,
                                int64_t* rowptr_out, int64_t* nnz_out, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------
+ * Mini-batch sampling on the device — replaces the CPU workers of
+ * torch_geometric.data.GraphSAINTRandomWalkSampler as the reference drives it (mag_pyg/gnn.py:361-366: roots uniform
+ * over the nodes, torch_sparse.random_walk of walk_length steps, SparseTensor.saint_subgraph of the visited nodes).
+ *   random_walk: out[w][0] = start[w]; step s of walker w moves to col[rowptr[v] + (r * deg >> 32)], r = word (s % 4) of
+ *     Philox4x32-10(seed, offset, w * ceil(L/4) + s / 4); a node without out-edges holds the walker.  out: [n_walks, L+1].
+ *   saint_subgraph: induced subgraph of the sorted unique node set `nodes` over CSR, CSR order kept.  count -> per selected
+ *     row the number of kept edges (and fills node_map, an int32 [n_nodes] workspace that holds -1 on entry); the caller
+ *     prefix-sums the counts into out_ptr; fill -> local row / local col / parent edge id (eid[j], or j when eid is NULL).
+ * ------------------------------------------------------------------ */
+int b200gnn_random_walk_i64(const int32_t* rowptr, const int32_t* col, int64_t n_nodes, const int64_t* start,
+                            int64_t n_walks, int32_t walk_length, uint64_t seed, uint64_t offset, int64_t* out,
+                            void* stream);
+int b200gnn_saint_subgraph_count_i64(const int32_t* rowptr, const int32_t* col, const int64_t* nodes, int64_t n_sel,
+                                     int32_t* node_map, int64_t* counts, void* stream);
+int b200gnn_saint_subgraph_fill_i64(const int32_t* rowptr, const int32_t* col, const int64_t* eid, const int64_t* nodes,
+                                    int64_t n_sel, const int32_t* node_map, const int64_t* out_ptr, int64_t* out_row,
+                                    int64_t* out_col, int64_t* out_eid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
