@@ -95,3 +95,31 @@ def mag_relation_edges(src_type: str, dst_type: str, num_edges: int, seed: int) 
     dst = (torch.rand(num_edges, generator=g, dtype=torch.float64).pow(3) * nd).long().clamp_(max=nd - 1)
     key = torch.unique(src * nd + dst)
     return torch.stack([key // nd, key % nd])
+
+
+# PPI shape (ppi_pyg/gnn.py:305-310): 24 protein graphs (20 train / 2 val / 2 test), ~2.4 k nodes and ~33 k directed edges
+# each (symmetric), 50 features, 121 multi-hot labels.
+PPI = dict(num_features=50, num_classes=121, n_graphs=dict(train=20, val=2, test=2), nodes=(1_500, 3_400), avg_degree=28)
+
+
+def make_ppi_graphs(split: str = "train", seed: int = 0, scale: float = 1.0):
+    """List of PPI-shaped small graphs as (x [n,50], y [n,121] float multi-hot, edge_index [2,e] symmetric) tuples.
+    Labels are a noisy linear function of the mean of a node's neighbourhood, so that a GNN can fit them."""
+    base = dict(train=0, val=1000, test=2000)[split]
+    out = []
+    for i in range(PPI["n_graphs"][split]):
+        g = torch.Generator().manual_seed(seed * 7919 + base + i)
+        lo, hi = PPI["nodes"]
+        n = max(8, int((lo + int(torch.randint(0, hi - lo, (1,), generator=g))) * scale))
+        e = n * PPI["avg_degree"] // 2
+        a, b = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+        keep = a != b
+        key = torch.unique(torch.cat([a[keep] * n + b[keep], b[keep] * n + a[keep]]))
+        ei = torch.stack([key // n, key % n])
+        x = torch.randn(n, PPI["num_features"], generator=g)
+        w = torch.randn(PPI["num_features"], PPI["num_classes"], generator=torch.Generator().manual_seed(seed))
+        agg = torch.zeros(n, PPI["num_features"]).index_add_(0, ei[1], x[ei[0]])
+        deg = torch.bincount(ei[1], minlength=n).clamp_(min=1).unsqueeze(1)
+        y = (((x + agg / deg) @ w + 0.3 * torch.randn(n, PPI["num_classes"], generator=g)) > 0.8).float()
+        out.append((x, y, ei))
+    return out
