@@ -598,7 +598,13 @@ class GATConv(torch.nn.Module):
         xl = self.lin_l(x).view(-1, H, C)
         al, ar = (xl * self.att_l).sum(-1), (xl * self.att_r).sum(-1)
         _, scale = _attention_masks(adj.storage.col().numel(), H, 0.0, self.dropout, self.training, x.device)
-        out = gat_aggregate(xl.reshape(-1, H * C), al, ar, adj, H, self.negative_slope, 1e-16, None, scale).view(-1, H, C)
+        # The aggregation kernels move whole 128-bit vectors inside a head: a head width that is not a multiple of 4 (PPI's 121
+        # classes, ppi_pyg/gnn.py:31,61) is zero-padded per head for the kernel and the padding sliced off again (exact).
+        Cp = (C + 3) // 4 * 4
+        ft = xl if Cp == C else F.pad(xl, (0, Cp - C))
+        out = gat_aggregate(ft.reshape(-1, H * Cp), al, ar, adj, H, self.negative_slope, 1e-16, None, scale).view(-1, H, Cp)
+        if Cp != C:
+            out = out[..., :C]
         out = out.reshape(-1, H * C) if self.concat else out.mean(dim=1)
         return out if self.bias is None else out + self.bias
 

@@ -50,6 +50,9 @@ class SaintGraph:
         """node_idx: sorted unique int64.  Returns (edge_index [2, e] in local ids, parent edge ids [e]), CSR order."""
         L = lib.load()
         n_sel = node_idx.numel()
+        if n_sel == 0:
+            z = torch.empty(0, dtype=torch.long, device=self.col.device)
+            return torch.empty(2, 0, dtype=torch.long, device=self.col.device), z
         counts = torch.empty(n_sel, dtype=torch.long, device=node_idx.device)
         lib.check(L.b200gnn_saint_subgraph_count_i64(self.rowptr.data_ptr(), self.col.data_ptr(), lib.dptr(node_idx, torch.long, "node_idx"),
                                                      n_sel, self.node_map.data_ptr(), counts.data_ptr(), lib.stream_ptr()),

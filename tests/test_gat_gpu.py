@@ -160,10 +160,11 @@ def test_dgl_gatconv_training_knobs_run_and_are_inert_in_eval():
 
 
 @pytest.mark.parametrize("concat", [True, False])
-def test_pyg_gatconv_gradients_and_head_mean(concat):
+@pytest.mark.parametrize("H,C", [(4, 12), (4, 121), (6, 121)])      # 121: PPI's class count — a head width that is not a multiple of 4
+def test_pyg_gatconv_gradients_and_head_mean(concat, H, C):
     """PyG GATConv as ppi_pyg/gnn.py:27-31 uses it (heads 4/6, last layer concat=False): forward and every gradient
     against the fp64 restatement (self-loops re-added, softmax eps 1e-16)."""
-    n, Fin, H, C = 700, 50, 4, 12
+    n, Fin = 700, 50
     ei = skewed_edges(n, 4000, 5)
     torch.manual_seed(2)
     layer = bnn.GATConv(Fin, C, heads=H, concat=concat).cuda()
