@@ -601,7 +601,7 @@ class GATConv(torch.nn.Module):
         # The aggregation kernels move whole 128-bit vectors inside a head: a head width that is not a multiple of 4 (PPI's 121
         # classes, ppi_pyg/gnn.py:31,61) is zero-padded per head for the kernel and the padding sliced off again (exact).
         Cp = (C + 3) // 4 * 4
-        ft = xl if Cp == C else F.pad(xl, (0, Cp - C))
+        ft = xl if Cp == C else torch.nn.functional.pad(xl, (0, Cp - C))
         out = gat_aggregate(ft.reshape(-1, H * Cp), al, ar, adj, H, self.negative_slope, 1e-16, None, scale).view(-1, H, Cp)
         if Cp != C:
             out = out[..., :C]

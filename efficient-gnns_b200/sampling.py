@@ -60,10 +60,11 @@ class SaintGraph:
         ptr = torch.cumsum(counts, 0) - counts
         e = int(counts.sum())                              # the batch's edge count sizes the outputs (one host read per batch)
         out = torch.empty(3, e, dtype=torch.long, device=node_idx.device)
-        lib.check(L.b200gnn_saint_subgraph_fill_i64(self.rowptr.data_ptr(), self.col.data_ptr(), self.eid.data_ptr(),
-                                                    node_idx.data_ptr(), n_sel, self.node_map.data_ptr(), ptr.data_ptr(),
-                                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), lib.stream_ptr()),
-                  "saint_subgraph_fill_i64")
+        if e > 0:
+            lib.check(L.b200gnn_saint_subgraph_fill_i64(self.rowptr.data_ptr(), self.col.data_ptr(), self.eid.data_ptr(),
+                                                        node_idx.data_ptr(), n_sel, self.node_map.data_ptr(), ptr.data_ptr(),
+                                                        out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), lib.stream_ptr()),
+                      "saint_subgraph_fill_i64")
         self.node_map[node_idx] = -1                       # restore the workspace for the next batch
         return out[:2], out[2]
 
