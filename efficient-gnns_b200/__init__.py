@@ -9,7 +9,11 @@ Layout
   nn.py        GCNConv / SAGEConv / MessagePassing mirrors of the PyG surface
   criterion.py fused distillation criteria (same names/arguments as the reference's criterion.py)
   engine.py    graph-captured full training step for the benchmark configs
-  dist.py      node-parallel sharding + halo exchange over NCCL
+  engine_sage.py / rgcn.py     fused GraphSAGE step, full-batch R-GCN inference
+  hybrid.py / peer.py / hybrid_gat.py   multi-GPU: node-parallel dense ops + feature-parallel aggregations, peer-memory exchange
+  dist.py      round-1 node-parallel engine (all-gather per aggregation), kept as the baseline
+  sampling.py  device-side GraphSAINT random-walk sampler, small-graph DataLoader
+  torch_ops.py `torch.ops.b200gnn.*` registration (import it to register; the module path does not need it)
   shim/        packages named torch_sparse / torch_scatter / torch_geometric / ogb
                re-exporting the above so the reference's scripts run unmodified
 
