@@ -372,9 +372,14 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 else:
                     ax = ops.spmm_csr(self.G, x_in, "sum", out=self.AX)
                 self._layer_in[0] = ax
-                self._linear(0, ax, self.Y[0], bias=self.b[0])
+                gp = self._gemm_part.get(k) if training else None
+                if gp is not None:                   # this rank's BatchNorm partial sums out of the GEMM epilogue (engine.py)
+                    hi, lo = ops.split_tf32(self.W[0], transpose=True, hi=self.Wt_split[0][0], lo=self.Wt_split[0][1])
+                    ops.gemm_tf32x3_stats(ax, hi, lo, self.b[0], self.Y[0], gp)
+                else:
+                    self._linear(0, ax, self.Y[0], bias=self.b[0])
                 if training:
-                    part = ops.col_stats(self.Y[0], partial=self._part(k))
+                    part = gp if gp is not None else ops.col_stats(self.Y[0], partial=self._part(k))
                     sums = self._row_stats_allgather(part, k)
                     ops.bn_finalize(sums, self.n_global, self.gamma[0], self.beta[0], self.bn_eps, self.bn_momentum,
                                     self.running_mean[0], self.running_var[0], out=self.bn[0])
@@ -487,6 +492,7 @@ class HybridGCNTrainer(GCNStudentTrainer):
         self.grads.zero_()                              # slices a rank does not own stay zero (summed over ranks later)
         d_act = None                                    # d loss / d A_{l-1} in R layout, produced by layer l's dgrad
         fused_prev = False                              # ... or already delivered in C layout by that GEMM's epilogue
+        dz_ready = False                                # ... or already masked + reduced by that GEMM's epilogue (R layout)
         for l in range(L - 1, -1, -1):
             k = dims[l + 1]
             last = l == L - 1
@@ -495,9 +501,14 @@ class HybridGCNTrainer(GCNStudentTrainer):
             if first_agg:
                 # BatchNorm backward in R layout with globally summed statistics, then dW0 = (ÂX)^T dY0
                 part, bn = self._part(k), self.bn[0]
-                ops.bn_act_bwd_reduce(d_act, self.A[0], self.Y[0], bn[0], bn[1], self.p, part)
-                sums = self._row_stats_allgather(part, k)
-                ops.bn_act_bwd_apply(d_act, self.A[0], self.Y[0], bn[0], bn[1], self.gamma[0], sums, self.n_global, self.p,
+                if dz_ready:                            # layer 1's input-gradient GEMM already stored dz and reduced it
+                    sums = self._row_stats_allgather(self._gemm_part[k], k)
+                    x_out = None
+                else:
+                    ops.bn_act_bwd_reduce(d_act, self.A[0], self.Y[0], bn[0], bn[1], self.p, part)
+                    sums = self._row_stats_allgather(part, k)
+                    x_out = self.A[0]
+                ops.bn_act_bwd_apply(d_act, x_out, self.Y[0], bn[0], bn[1], self.gamma[0], sums, self.n_global, self.p,
                                      self.dY[0], self.ggamma[0], self.gbeta[0], self.gb[0], part, self._coef(k))
                 if self.rank != 0:                      # computed from GLOBAL sums on every rank: count once
                     self.ggamma[0].zero_(); self.gbeta[0].zero_()
@@ -546,6 +557,12 @@ class HybridGCNTrainer(GCNStudentTrainer):
                 if (not prev_first_agg) and self.col_mode[k_prev] and (l - 1 < L - 1) and self._fusable(k_prev):
                     self._dgrad_r2c(l, dH, f"dAc{l - 1}")   # input-gradient GEMM epilogue = the R->C exchange of d A_{l-1}
                     fused_prev, d_act = True, None
+                elif prev_first_agg and self._gemm_part.get(k_prev) is not None:
+                    # layer 0's BatchNorm lives in R layout: pass 1 of its backward in this GEMM's epilogue (engine.py)
+                    hi, lo = ops.split_tf32(self.W[l], transpose=False, hi=self.W_split[l][0], lo=self.W_split[l][1])
+                    ops.gemm_tf32x3_bnbwd(dH, hi, lo, self.dA[0], self.A[0], self.Y[0], self.bn[0][0], self.bn[0][1], self.p,
+                                          self._gemm_part[k_prev])
+                    d_act, dz_ready = self.dA[0], True
                 else:
                     self._linear_dgrad(l, dH, self.dA[l - 1])
                     d_act = self.dA[l - 1]
