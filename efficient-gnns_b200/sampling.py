@@ -80,8 +80,13 @@ class GraphSAINTRandomWalkSampler:
             raise NotImplementedError("sample_coverage > 0 (node/edge normalisation statistics): the reference passes 0 "
                                       "(mag_pyg/gnn.py:365)")
         if not data.edge_index.is_cuda:
-            raise lib.B200GnnError("GraphSAINTRandomWalkSampler: the parent graph must live on the CUDA device (move the "
-                                   "Data object with .to(device) before building the sampler); there is no CPU fallback")
+            # the reference builds the sampler on a host-resident Data (mag_pyg/gnn.py:361) and moves every batch (:188); here
+            # the PARENT graph is uploaded once and batches are born on the device — sampling itself never runs on the CPU
+            if not torch.cuda.is_available():
+                raise lib.B200GnnError("GraphSAINTRandomWalkSampler: sampling runs on the CUDA device and none is available; "
+                                       "there is no CPU fallback")
+            import copy
+            data = copy.copy(data).to(torch.device("cuda", torch.cuda.current_device()))
         self.data = data
         self.N, self.E = int(data.num_nodes), int(data.edge_index.size(1))
         self.batch_size, self.walk_length, self.num_steps = int(batch_size), int(walk_length), int(num_steps)

@@ -123,3 +123,32 @@ def make_ppi_graphs(split: str = "train", seed: int = 0, scale: float = 1.0):
         y = (((x + agg / deg) @ w + 0.3 * torch.randn(n, PPI["num_classes"], generator=g)) > 0.8).float()
         out.append((x, y, ei))
     return out
+
+
+def make_mag_dataset(scale: float = 1.0, seed: int = 0, num_features: int = 128, num_classes: int = 349):
+    """Heterogeneous ogbn-mag-SHAPED synthetic (mag_pyg/gnn.py:308-321 reads these fields): the four directed relations of
+    MAG_RELATIONS between MAG_NODES node types (reverse relations / the undirected paper-paper view are added by the caller,
+    as the reference's main() does), 128-d features on papers only, 349 venue labels on papers, a random train/valid/test
+    split of the papers.  ``scale`` shrinks every count (tests, plumbing runs)."""
+    g = torch.Generator().manual_seed(seed + 17)
+    nodes = {k: max(4, int(v * scale)) for k, v in MAG_NODES.items()}
+    edge_index_dict = {}
+    for i, ((s_t, rel, d_t), e) in enumerate(MAG_RELATIONS.items()):
+        ne = max(8, int(e * scale))
+        ns, nd = nodes[s_t], nodes[d_t]
+        src = torch.randint(0, ns, (ne,), generator=g)
+        dst = (torch.rand(ne, generator=g, dtype=torch.float64).pow(3) * nd).long().clamp_(max=nd - 1)
+        if s_t == d_t:
+            keep = src != dst
+            src, dst = src[keep], dst[keep]
+        key = torch.unique(src * nd + dst)
+        edge_index_dict[(s_t, rel, d_t)] = torch.stack([key // nd, key % nd])
+    n_paper = nodes["paper"]
+    x = torch.randn(n_paper, num_features, generator=g)
+    y = torch.randint(0, num_classes, (n_paper, 1), generator=g)
+    perm = torch.randperm(n_paper, generator=g)
+    a, b = int(0.85 * n_paper), int(0.94 * n_paper)
+    split = {"train": {"paper": perm[:a].sort().values}, "valid": {"paper": perm[a:b].sort().values},
+             "test": {"paper": perm[b:].sort().values}}
+    return dict(num_nodes_dict=nodes, edge_index_dict=edge_index_dict, x_dict={"paper": x}, y_dict={"paper": y},
+                split_idx=split, num_classes=num_classes)

@@ -54,6 +54,15 @@ def test_oracle_walk_is_uniform_over_neighbours():
     assert np.abs(freq - 0.25).max() < 0.01
 
 
+def test_sampler_without_a_gpu_raises_instead_of_sampling_on_the_cpu():
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only environment")
+    d = Data(edge_index=torch.randint(0, 10, (2, 30)))
+    d.num_nodes = 10
+    with pytest.raises(Exception, match="no CPU fallback"):
+        sampling.GraphSAINTRandomWalkSampler(d, batch_size=4)
+
+
 def test_small_graph_batches_cpu():
     """DataLoader over PPI-like graphs (ppi_pyg/gnn.py:305-310): disjoint union, offsets, graph ids."""
     gs = []
@@ -128,8 +137,9 @@ def test_graphsaint_sampler_batches_like_the_reference_loop():
                 local_node_idx=torch.arange(n), train_mask=torch.rand(n, generator=g) < 0.3, y=torch.randint(0, 9, (n,), generator=g),
                 num_classes=9)
     data.num_nodes = n
-    with pytest.raises(Exception):
-        sampling.GraphSAINTRandomWalkSampler(data, batch_size=10)            # CPU parent graph: refused, no fallback
+    host_loader = sampling.GraphSAINTRandomWalkSampler(data, batch_size=10, walk_length=1, num_steps=1)   # host-resident parent, as
+    b0 = next(iter(host_loader))                                         # mag_pyg/gnn.py:361 builds it: uploaded once,
+    assert b0.edge_index.is_cuda and b0.y.is_cuda and not data.edge_index.is_cuda   # batches are born on the device
     data = data.to("cuda")
     loader = sampling.GraphSAINTRandomWalkSampler(data, batch_size=500, walk_length=2, num_steps=3, sample_coverage=0, seed=7)
     assert len(loader) == 3

@@ -66,3 +66,40 @@ def test_subgraph_and_hetero_match_oracle(shim_path):
     assert e.tolist() == [[0, 1, 3], [4, 2, 1]] and et.tolist() == [0, 0, 1] and nt.tolist() == [0, 0, 1, 1, 1]
     assert li.tolist() == [0, 1, 0, 1, 2] and k2i["b"] == 1 and k2i[("b", "s", "a")] == 1
     assert l2g["a"].tolist() == [0, 1] and l2g["b"].tolist() == [2, 3, 4]
+
+
+def test_mag_shaped_dataset_and_grouping_as_the_reference_main_uses_them():
+    """mag_pyg/gnn.py:308-356 up to the sampler: dataset fields, reverse relations, to_undirected, group_hetero_graph, the
+    homogeneous Data with labels and train mask."""
+    import sys
+    from pathlib import Path
+    import torch
+    import efficient_gnns_b200
+    sys.path.insert(0, str(Path(efficient_gnns_b200.__file__).resolve().parent / "shim"))
+    try:
+        from ogb.nodeproppred import PygNodePropPredDataset
+        from torch_geometric.data import Data
+        from torch_geometric.utils.hetero import group_hetero_graph
+        dataset = PygNodePropPredDataset(name="ogbn-mag-plumbing")
+        data = dataset[0]
+        split_idx = dataset.get_idx_split()
+        assert dataset.num_classes == 349 and set(data.x_dict) == {"paper"} and data.x_dict["paper"].shape[1] == 128
+        eid = data.edge_index_dict
+        assert set(eid) == {("author", "affiliated_with", "institution"), ("author", "writes", "paper"),
+                            ("paper", "cites", "paper"), ("paper", "has_topic", "field_of_study")}
+        r, c = eid[("author", "writes", "paper")]
+        assert int(r.max()) < data.num_nodes_dict["author"] and int(c.max()) < data.num_nodes_dict["paper"]
+        eid[("paper", "to", "author")] = torch.stack([c, r])
+        out = group_hetero_graph(eid, data.num_nodes_dict)
+        edge_index, edge_type, node_type, local_node_idx, local2global, key2int = out
+        n = sum(data.num_nodes_dict.values())
+        assert node_type.numel() == n and int(edge_index.max()) < n and int(edge_type.max()) == 4
+        homo = Data(edge_index=edge_index, edge_attr=edge_type, node_type=node_type, local_node_idx=local_node_idx, num_nodes=n)
+        homo.y = node_type.new_full((n, 1), -1)
+        homo.y[local2global["paper"]] = data.y_dict["paper"]
+        homo.train_mask = torch.zeros(n, dtype=torch.bool)
+        homo.train_mask[local2global["paper"][split_idx["train"]["paper"]]] = True
+        assert homo.num_nodes == n and int(homo.train_mask.sum()) == split_idx["train"]["paper"].numel()
+        assert bool((homo.y[homo.train_mask] >= 0).all())
+    finally:
+        sys.path.pop(0)
